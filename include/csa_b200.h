@@ -1,0 +1,156 @@
+/*
+ * csa_b200 — C ABI of the B200-native Consistent Self-Attention hot path.
+ *
+ * This is the drop-in boundary for the one data-parallel path of Layjins/Spider's story generation
+ * (StoryDiffusion's `SpatialAttnProcessor2_0` + `cal_attn_mask_xl` + `id_bank`).  The reference has no FFI on
+ * this path — it is pure PyTorch — so each entry point below replaces a *library call site* of the reference
+ * (file:line relative to the reference tree) and is bound from Python with ctypes:
+ *
+ *   csa_compact_rows      <- StoryDiffusion/utils/gradio_utils.py:260-286  (dense (T*N)^2 bool mask build) and the
+ *                            mask slicing at StoryDiffusion/Comic_Generation.py:105-114: instead of materialising
+ *                            the mask, the per-frame rows are compacted into ascending key index lists
+ *                            (== torch.nonzero(mask[f*N]), bit-exact).
+ *   csa_validate_mask     <- the premise of the compaction (all N rows of a frame block are identical), checked on
+ *                            a dense mask supplied by an unmodified driver (Comic_Generation.py:376).
+ *   csa_attn_fwd          <- F.scaled_dot_product_attention(q, k, v, attn_mask=mask) at
+ *                            Comic_Generation.py:175-177 (consistent) and :248-250 (standard / read-early), plus the
+ *                            torch.cat of bank and current frames at :92 (two K/V sources are read in place).
+ *   csa_gather_rows       <- the row selection implied by the mask when K/V rows have to be materialised
+ *                            contiguously (multi-GPU exchange of the sampled rows; bank export).
+ *
+ * Conventions: all pointers are DEVICE pointers unless stated; no function allocates, frees or synchronises;
+ * `stream` is a cudaStream_t passed as void*; every function returns 0 on success, a negative CSA_E_* on a bad
+ * argument, or a positive cudaError_t / CUresult from the runtime.  csa_last_error() describes the last failure
+ * on the calling thread.  There is no CPU fallback anywhere in this library.
+ */
+#ifndef CSA_B200_H_
+#define CSA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSA_ABI_VERSION 1
+
+#define CSA_E_BADARG (-1)   /* null pointer, non-positive size, misaligned pointer/stride */
+#define CSA_E_SHAPE (-2)    /* unsupported geometry (head_dim != 64, row stride not 16-byte aligned, ...) */
+#define CSA_E_DEVICE (-3)   /* not an sm_100 device */
+#define CSA_E_DRIVER (-4)   /* could not resolve cuTensorMapEncodeTiled */
+
+#define CSA_DTYPE_F16 0
+#define CSA_DTYPE_BF16 1
+
+#define CSA_HEAD_DIM 64
+#define CSA_TILE 128 /* keys per tile; index-list rows must be padded to a multiple of this */
+
+int csa_abi_version(void);
+const char* csa_last_error(void);
+
+/* 0 if `device` is an sm_100 part this library can run on, CSA_E_DEVICE otherwise. */
+int csa_device_supported(int device);
+
+/* If a kernel trapped on its barrier watchdog, copies {tag, block, thread, parity} to out[4] (HOST pointer)
+ * and returns 1; returns 0 if nothing is recorded.  Synchronises the device.  Debug aid only. */
+int csa_debug_stuck(uint32_t* out4_host);
+
+/*
+ * Compact `n_rows` boolean rows of `n_cols` bytes each into ascending column index lists.
+ *   mask        row r starts at mask + r*row_stride bytes; byte != 0 means "attend".  row_stride may be 0
+ *               (every row is the same sampled vector, cf. gradio_utils.py:257-261).
+ *   block_n     if > 0, row r additionally gets its own block [r*block_n, (r+1)*block_n) forced True and every
+ *               column >= limit_cols outside that block forced False (gradio_utils.py:267-278); if 0 the bytes
+ *               are used as they are (a row of an already-built dense mask).
+ *   idx         out, row r at idx + r*idx_stride int32s; idx_stride must be a multiple of 4 and >= n_cols rounded
+ *               up to CSA_TILE; entries at and beyond counts[r] are left untouched.
+ *   counts      out, n_rows int32.
+ */
+int csa_compact_rows(const uint8_t* mask, int64_t row_stride, int32_t n_rows, int32_t n_cols, int32_t block_n,
+                     int32_t limit_cols, int32_t* idx, int64_t idx_stride, int32_t* counts, void* stream);
+
+/*
+ * Check that a dense (n_rows x n_cols) bool mask, row stride `row_stride` bytes, consists of blocks of `block_n`
+ * identical consecutive rows.  *n_bad (device int32, must be zeroed by the caller) receives the number of 16-byte
+ * words that differ from the first row of their block.  HBM-bound: reads the mask once.
+ */
+int csa_validate_mask(const uint8_t* mask, int64_t row_stride, int32_t n_rows, int32_t n_cols, int32_t block_n,
+                      int32_t* n_bad, void* stream);
+
+/*
+ * dst[i, :] = src[row_base + idx[i], :] for i < min(*count + count_adjust, max_rows); rows are `row_bytes` wide
+ * (multiple of 16), leading dimensions in bytes.  `count` is a device pointer so no host sync is needed.
+ */
+int csa_gather_rows(const void* src, int64_t src_ld_bytes, int32_t row_base, const int32_t* idx,
+                    const int32_t* count, int32_t count_adjust, int32_t max_rows, void* dst, int64_t dst_ld_bytes,
+                    int32_t row_bytes, void* stream);
+
+/*
+ * Flash attention over compacted keys, head_dim 64, fp16 or bf16 in/out, fp32 softmax and accumulation.
+ *
+ * Work is organised as n_groups (the CFG halves, which never mix: Comic_Generation.py:148) x n_frames query
+ * frames x heads.  Queries of (group g, frame f) are rows [(g*n_frames + f)*n_q, +n_q) of `q`; head h is columns
+ * [64h, 64h+64).  `o` is indexed like `q`.  The keys of (g, f) are the concatenation of up to three segments:
+ *
+ *   gathered    rows  g*a_group_rows + idx[list][0 .. counts[list] + g_adjust)  of k_a / v_a,
+ *               list = list_base + f*list_step  (disabled when list_base < 0)
+ *   contig A    rows  g*a_group_rows + ca_start + f*ca_step + [0, ca_len)        of k_a / v_a
+ *   contig B    rows  g*b_group_rows + cb_start + f*cb_step + [0, cb_len)        of k_b / v_b
+ *
+ * which covers the four branches of the reference processor:
+ *   write, consistent (:129-196)   gathered with list f over A = this call's K/V          (mask[:F*N,:F*N])
+ *   read, consistent               gathered list F minus the own block (g_adjust = -N) over A = id_bank K/V,
+ *                                  contig B = this call's K/V                                  (mask[F*N:])
+ *   read, early steps (:94-96)     contig A = all F*N bank rows, contig B = own frame
+ *   standard (:198-268, enc=None)  contig B = own frame
+ * Softmax is permutation invariant, so the segment order need not equal the reference's key order.
+ */
+typedef struct csa_attn_args {
+  uint32_t struct_size; /* sizeof(csa_attn_args_t), checked */
+  int32_t dtype;        /* CSA_DTYPE_* */
+  int32_t head_dim;     /* must be 64 */
+  int32_t heads;
+  int32_t n_groups;
+  int32_t n_frames;
+  int32_t n_q;
+  float scale; /* softmax scale, 1/sqrt(head_dim) in the reference (SDPA default) */
+
+  const void* q;
+  void* o;
+  int64_t q_ld; /* row strides in elements */
+  int64_t o_ld;
+
+  const void* k_a;
+  const void* v_a;
+  int64_t a_ld;
+  int64_t a_rows; /* total rows addressable in A (TMA bound) */
+  int32_t a_group_rows;
+  int32_t _pad0;
+
+  const void* k_b;
+  const void* v_b;
+  int64_t b_ld;
+  int64_t b_rows;
+  int32_t b_group_rows;
+  int32_t _pad1;
+
+  const int32_t* idx;
+  const int32_t* counts;
+  int64_t idx_stride;
+  int32_t list_base;
+  int32_t list_step;
+  int32_t g_adjust;
+
+  int32_t ca_start, ca_step, ca_len;
+  int32_t cb_start, cb_step, cb_len;
+
+  int32_t max_ctas; /* 0 = one per SM */
+  int32_t flags;    /* reserved, 0 */
+} csa_attn_args_t;
+
+int csa_attn_fwd(const csa_attn_args_t* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSA_B200_H_ */

@@ -1,0 +1,583 @@
+// Consistent Self-Attention forward for B200 (sm_100a): flash attention over compacted key lists.
+//
+// Replaces F.scaled_dot_product_attention(q, k, v, attn_mask=dense_bool) of the reference
+// (StoryDiffusion/Comic_Generation.py:175-177 and :248-250).  Because the sampled mask row is shared by every query
+// of a frame (StoryDiffusion/utils/gradio_utils.py:257-286), the dense mask is never built: each (CFG half, frame)
+// attends a *key list* = TMA-gathered sampled rows + contiguous rows, see include/csa_b200.h.
+//
+// One persistent CTA per SM, 384 threads, warp-specialised:
+//   warp 0      producer   TMA: Q tiles (box 64x128), K/V tiles either as one tiled load (contiguous run of keys) or
+//                          as 32 lane-parallel `tile::gather4` loads (4 indexed rows each) into the same 128B-swizzled
+//                          16 KB stage
+//   warp 1      MMA issue  one lane issues tcgen05.mma:  S = Q K^T  (SS, M128 N128 K64),  O += P V (TS: P read from
+//                          TMEM as the A operand, V read MN-major from the very tile TMA wrote, M128 N64 K128)
+//   warp 2      TMEM allocator (512 columns: S0 S1 | O0 O1 | P0 P1)
+//   warps 4-7   softmax for Q tile 0 (thread == query row, no shuffles), warps 8-11 for Q tile 1.
+//               online softmax in the exp2 domain with lazy (threshold 8) rescaling of O, P written to TMEM as
+//               16-bit, final 1/l normalisation and store.
+// Two 128-row Q tiles are ping-ponged so that the tensor core works on one tile while the other is in softmax.
+#include "ptx.cuh"
+#include "csa_internal.h"
+
+namespace csa {
+
+constexpr int kBM = 128;  // query rows per Q tile
+constexpr int kBN = 128;  // keys per K/V tile
+constexpr int kHD = 64;   // head dim
+constexpr int kTileBytes = kBN * kHD * 2;
+constexpr int kKStages = 4;
+constexpr int kVStages = 4;
+constexpr int kThreads = 384;
+
+// TMEM column map (fp32 columns)
+constexpr uint32_t kColS = 0;    // S0 at 0, S1 at 128
+constexpr uint32_t kColO = 256;  // O0 at 256, O1 at 320
+constexpr uint32_t kColP = 384;  // P0 at 384, P1 at 448 (128 16-bit values = 64 columns)
+
+struct __align__(1024) AttnSmem {
+  uint8_t q[2][kTileBytes];
+  uint8_t k[kKStages][kTileBytes];
+  uint8_t v[kVStages][kTileBytes];
+  uint64_t q_full[2], q_empty[2];
+  uint64_t k_full[kKStages], k_empty[kKStages];
+  uint64_t v_full[kVStages], v_empty[kVStages];
+  uint64_t s_full[2], p_ready[2], o_done[2];
+  uint32_t tmem_base;
+};
+
+struct AttnKernelParams {
+  CUtensorMap tm_q;    // box 64 x 128
+  CUtensorMap tm_ka;   // box 64 x 128, source A
+  CUtensorMap tm_va;
+  CUtensorMap tm_kag;  // box 64 x 1 (gather4), source A
+  CUtensorMap tm_vag;
+  CUtensorMap tm_kb;   // box 64 x 128, source B
+  CUtensorMap tm_vb;
+  void* o;
+  int64_t o_ld;
+  const int32_t* idx;
+  const int32_t* counts;
+  int64_t idx_stride;
+  int32_t heads, n_groups, n_frames, n_q, n_qpairs, n_units;
+  int32_t a_group_rows, b_group_rows;
+  int32_t list_base, list_step, g_adjust;
+  int32_t ca_start, ca_step, ca_len;
+  int32_t cb_start, cb_step, cb_len;
+  float scale_log2;
+  uint32_t* dbg;  // host-mapped watchdog record (may be null)
+};
+
+struct Unit {
+  int g, f, h, qp;
+  int q_row0;  // first query row (in the q / o matrices) of the pair of Q tiles
+  int ng;      // gathered keys
+  const int32_t* gidx;
+  int a_base;  // row offset of this group in A
+  int ca_row, ca_len;
+  int cb_row, cb_len;
+  int tg, ta, tb, total;
+};
+
+__device__ __forceinline__ Unit decode_unit(const AttnKernelParams& p, int u) {
+  Unit w;
+  w.qp = u % p.n_qpairs;
+  int r = u / p.n_qpairs;
+  w.h = r % p.heads;
+  r /= p.heads;
+  w.f = r % p.n_frames;
+  w.g = r / p.n_frames;
+  w.q_row0 = (w.g * p.n_frames + w.f) * p.n_q + w.qp * (2 * kBM);
+  w.ng = 0;
+  w.gidx = nullptr;
+  if (p.list_base >= 0) {
+    const int list = p.list_base + w.f * p.list_step;
+    int c = __ldg(p.counts + list) + p.g_adjust;
+    w.ng = c > 0 ? c : 0;
+    w.gidx = p.idx + static_cast<int64_t>(list) * p.idx_stride;
+  }
+  w.a_base = w.g * p.a_group_rows;
+  w.ca_row = w.a_base + p.ca_start + w.f * p.ca_step;
+  w.ca_len = p.ca_len;
+  w.cb_row = w.g * p.b_group_rows + p.cb_start + w.f * p.cb_step;
+  w.cb_len = p.cb_len;
+  w.tg = (w.ng + kBN - 1) / kBN;
+  w.ta = (w.ca_len + kBN - 1) / kBN;
+  w.tb = (w.cb_len + kBN - 1) / kBN;
+  w.total = w.tg + w.ta + w.tb;
+  return w;
+}
+
+// number of valid keys in tile t of the unit
+__device__ __forceinline__ int tile_valid(const Unit& w, int t) {
+  int rem;
+  if (t < w.tg) {
+    rem = w.ng - t * kBN;
+  } else if (t < w.tg + w.ta) {
+    rem = w.ca_len - (t - w.tg) * kBN;
+  } else {
+    rem = w.cb_len - (t - w.tg - w.ta) * kBN;
+  }
+  return rem < kBN ? rem : kBN;
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_constant__ AttnKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  AttnSmem& sm = *reinterpret_cast<AttnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_q);
+    tma_prefetch_desc(&p.tm_ka);
+    tma_prefetch_desc(&p.tm_va);
+    tma_prefetch_desc(&p.tm_kag);
+    tma_prefetch_desc(&p.tm_vag);
+    tma_prefetch_desc(&p.tm_kb);
+    tma_prefetch_desc(&p.tm_vb);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&sm.q_full[i]), 1);
+      mbar_init(smem_u32(&sm.q_empty[i]), 1);
+      mbar_init(smem_u32(&sm.s_full[i]), 1);
+      mbar_init(smem_u32(&sm.p_ready[i]), kBM);
+      mbar_init(smem_u32(&sm.o_done[i]), 1);
+    }
+    for (int i = 0; i < kKStages; ++i) {
+      mbar_init(smem_u32(&sm.k_full[i]), 1);
+      mbar_init(smem_u32(&sm.k_empty[i]), 1);
+    }
+    for (int i = 0; i < kVStages; ++i) {
+      mbar_init(smem_u32(&sm.v_full[i]), 1);
+      mbar_init(smem_u32(&sm.v_empty[i]), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<512>(smem_u32(&sm.tmem_base));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // =========================================================================================== producer
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0, qph = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const Unit w = decode_unit(p, u);
+      if (w.total == 0) continue;
+      const int col = w.h * kHD;
+      if (lane == 0) {
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(smem_u32(&sm.q_empty[s]), qph ^ 1, 0x100 + s, p.dbg);
+          mbar_arrive_expect_tx(smem_u32(&sm.q_full[s]), kTileBytes);
+          tma_load_2d(&p.tm_q, smem_u32(sm.q[s]), smem_u32(&sm.q_full[s]), col, w.q_row0 + s * kBM);
+        }
+      }
+      qph ^= 1;
+      int last_idx = 0;
+      if (w.ng > 0) last_idx = __ldg(w.gidx + w.ng - 1);
+
+      for (int t = 0; t < w.total; ++t) {
+        // decide how tile t is fetched
+        bool gather = false;
+        const CUtensorMap* mk;
+        const CUtensorMap* mv;
+        int row0 = 0;
+        int4 iv = make_int4(0, 0, 0, 0);
+        if (t < w.tg) {
+          const int valid = min(kBN, w.ng - t * kBN);
+          const int pos = t * kBN + lane * 4;
+          iv = __ldg(reinterpret_cast<const int4*>(w.gidx + pos));
+          if (pos + 0 >= w.ng) iv.x = last_idx;
+          if (pos + 1 >= w.ng) iv.y = last_idx;
+          if (pos + 2 >= w.ng) iv.z = last_idx;
+          if (pos + 3 >= w.ng) iv.w = last_idx;
+          // contiguous run?  (lists are strictly ascending, so first/last decide)
+          const int first = __shfl_sync(0xffffffffu, iv.x, 0);
+          const int lpos = valid - 1;
+          const int src_lane = lpos >> 2;
+          const int c0 = __shfl_sync(0xffffffffu, iv.x, src_lane);
+          const int c1 = __shfl_sync(0xffffffffu, iv.y, src_lane);
+          const int c2 = __shfl_sync(0xffffffffu, iv.z, src_lane);
+          const int c3 = __shfl_sync(0xffffffffu, iv.w, src_lane);
+          const int sel = lpos & 3;
+          const int lastv = sel == 0 ? c0 : (sel == 1 ? c1 : (sel == 2 ? c2 : c3));
+          gather = (lastv - first) != lpos;
+          row0 = w.a_base + first;
+          mk = gather ? &p.tm_kag : &p.tm_ka;
+          mv = gather ? &p.tm_vag : &p.tm_va;
+          iv.x += w.a_base;
+          iv.y += w.a_base;
+          iv.z += w.a_base;
+          iv.w += w.a_base;
+        } else if (t < w.tg + w.ta) {
+          row0 = w.ca_row + (t - w.tg) * kBN;
+          mk = &p.tm_ka;
+          mv = &p.tm_va;
+        } else {
+          row0 = w.cb_row + (t - w.tg - w.ta) * kBN;
+          mk = &p.tm_kb;
+          mv = &p.tm_vb;
+        }
+        // ---- K
+        if (lane == 0) {
+          mbar_wait(smem_u32(&sm.k_empty[ks]), kph ^ 1, 0x110, p.dbg);
+          mbar_arrive_expect_tx(smem_u32(&sm.k_full[ks]), kTileBytes);
+        }
+        __syncwarp();
+        if (gather) {
+          tma_gather4(mk, smem_u32(sm.k[ks]) + lane * 512, smem_u32(&sm.k_full[ks]), col, iv.x, iv.y, iv.z, iv.w);
+        } else if (lane == 0) {
+          tma_load_2d(mk, smem_u32(sm.k[ks]), smem_u32(&sm.k_full[ks]), col, row0);
+        }
+        if (++ks == kKStages) { ks = 0; kph ^= 1; }
+        // ---- V
+        if (lane == 0) {
+          mbar_wait(smem_u32(&sm.v_empty[vs]), vph ^ 1, 0x120, p.dbg);
+          mbar_arrive_expect_tx(smem_u32(&sm.v_full[vs]), kTileBytes);
+        }
+        __syncwarp();
+        if (gather) {
+          tma_gather4(mv, smem_u32(sm.v[vs]) + lane * 512, smem_u32(&sm.v_full[vs]), col, iv.x, iv.y, iv.z, iv.w);
+        } else if (lane == 0) {
+          tma_load_2d(mv, smem_u32(sm.v[vs]), smem_u32(&sm.v_full[vs]), col, row0);
+        }
+        if (++vs == kVStages) { vs = 0; vph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================================================== MMA issue
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(kBM, kBN, kBF16 ? 1 : 0, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(kBM, kHD, kBF16 ? 1 : 0, 0, 1);
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0, qph = 0, pph0 = 0, pph1 = 0;
+      const uint32_t tS0 = tmem + kColS, tS1 = tmem + kColS + kBN;
+      const uint32_t tO0 = tmem + kColO, tO1 = tmem + kColO + kHD;
+      const uint32_t tP0 = tmem + kColP, tP1 = tmem + kColP + kBN / 2;
+
+      auto issue_qk = [&](int s, int kstage) {
+        const uint64_t dq = make_sw128_desc(smem_u32(sm.q[s]));
+        const uint64_t dk = make_sw128_desc(smem_u32(sm.k[kstage]));
+#pragma unroll
+        for (int kk = 0; kk < kHD / 16; ++kk) {
+          // advance 16 elements (32 B) along the contraction dim inside the swizzled 128 B row
+          mma_ss(s == 0 ? tS0 : tS1, dq + kk * 2, dk + kk * 2, idesc_qk, kk > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int s, int vstage, bool acc) {
+        const uint64_t dv = make_sw128_desc(smem_u32(sm.v[vstage]));
+#pragma unroll
+        for (int kk = 0; kk < kBN / 16; ++kk) {
+          // 16 keys = 16 rows of 128 B = 2048 B along the contraction dim (MN-major B operand);
+          // 16 16-bit P values = 8 TMEM columns
+          mma_ts(s == 0 ? tO0 : tO1, (s == 0 ? tP0 : tP1) + kk * 8, dv + kk * (2048 >> 4), idesc_pv,
+                 (acc || kk > 0) ? 1u : 0u);
+        }
+      };
+
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const Unit w = decode_unit(p, u);
+        if (w.total == 0) continue;
+        // prologue: S0 = Q0 K0^T, S1 = Q1 K0^T
+        mbar_wait(smem_u32(&sm.q_full[0]), qph, 0x200, p.dbg);
+        mbar_wait(smem_u32(&sm.k_full[ks]), kph, 0x201, p.dbg);
+        tc_fence_after();
+        issue_qk(0, ks);
+        tc_commit(smem_u32(&sm.s_full[0]));
+        if (w.total == 1) tc_commit(smem_u32(&sm.q_empty[0]));
+        mbar_wait(smem_u32(&sm.q_full[1]), qph, 0x202, p.dbg);
+        tc_fence_after();
+        issue_qk(1, ks);
+        tc_commit(smem_u32(&sm.s_full[1]));
+        tc_commit(smem_u32(&sm.k_empty[ks]));
+        if (w.total == 1) tc_commit(smem_u32(&sm.q_empty[1]));
+        if (++ks == kKStages) { ks = 0; kph ^= 1; }
+        qph ^= 1;
+
+        for (int j = 0; j < w.total; ++j) {
+          const bool more = (j + 1 < w.total);
+          const bool last_qk = (j + 2 == w.total);
+          mbar_wait(smem_u32(&sm.v_full[vs]), vph, 0x210, p.dbg);
+          mbar_wait(smem_u32(&sm.p_ready[0]), pph0, 0x211, p.dbg);
+          pph0 ^= 1;
+          tc_fence_after();
+          issue_pv(0, vs, j > 0);
+          tc_commit(smem_u32(&sm.o_done[0]));
+          if (more) {
+            mbar_wait(smem_u32(&sm.k_full[ks]), kph, 0x212, p.dbg);
+            tc_fence_after();
+            issue_qk(0, ks);
+            tc_commit(smem_u32(&sm.s_full[0]));
+            if (last_qk) tc_commit(smem_u32(&sm.q_empty[0]));
+          }
+          mbar_wait(smem_u32(&sm.p_ready[1]), pph1, 0x213, p.dbg);
+          pph1 ^= 1;
+          tc_fence_after();
+          issue_pv(1, vs, j > 0);
+          tc_commit(smem_u32(&sm.o_done[1]));
+          tc_commit(smem_u32(&sm.v_empty[vs]));
+          if (++vs == kVStages) { vs = 0; vph ^= 1; }
+          if (more) {
+            issue_qk(1, ks);
+            tc_commit(smem_u32(&sm.s_full[1]));
+            tc_commit(smem_u32(&sm.k_empty[ks]));
+            if (last_qk) tc_commit(smem_u32(&sm.q_empty[1]));
+            if (++ks == kKStages) { ks = 0; kph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =========================================================================================== softmax
+    const int s = (warp - 4) >> 2;              // Q tile of this warpgroup
+    const int row = ((warp & 3) << 5) | lane;   // query row inside the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) << 5) << 16;
+    const uint32_t tS = tmem + lane_base + kColS + s * kBN;
+    const uint32_t tO = tmem + lane_base + kColO + s * kHD;
+    const uint32_t tP = tmem + lane_base + kColP + s * (kBN / 2);
+    const uint32_t bar_s = smem_u32(&sm.s_full[s]);
+    const uint32_t bar_p = smem_u32(&sm.p_ready[s]);
+    const uint32_t bar_o = smem_u32(&sm.o_done[s]);
+    const float sc = p.scale_log2;
+    uint32_t sph = 0;
+    uint32_t od = 0;  // PV completions on o_done[s] before the current unit
+
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const Unit w = decode_unit(p, u);
+      const int q_in_frame = w.qp * (2 * kBM) + s * kBM + row;
+      const bool row_ok = q_in_frame < p.n_q;
+      uint4* optr = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
+                                             static_cast<int64_t>(w.q_row0 + s * kBM + row) * p.o_ld + w.h * kHD);
+      if (w.total == 0) {
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) optr[i] = make_uint4(0, 0, 0, 0);
+        }
+        continue;
+      }
+      float m = -INFINITY;  // running max, already multiplied by scale*log2(e)
+      float l = 0.f;
+
+      for (int j = 0; j < w.total; ++j) {
+        mbar_wait(bar_s, sph, 0x300 + s, p.dbg);
+        sph ^= 1;
+        tc_fence_after();
+        uint32_t sv[4][32];
+        tmem_ld32(tS + 0, sv[0]);
+        tmem_ld32(tS + 32, sv[1]);
+        tmem_ld32(tS + 64, sv[2]);
+        tmem_ld32(tS + 96, sv[3]);
+        tc_wait_ld();
+
+        const int valid = tile_valid(w, j);
+        if (valid < kBN) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
+        const float m_new = fmaxf(m, mx * sc);
+
+        if (j == 0) {
+          m = m_new;
+        } else {
+          const bool need = m_new > m + 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            // O still holds the accumulation up to tile j-1: make sure that MMA has retired, then rescale.
+            mbar_wait(bar_o, (od + j - 1) & 1, 0x310 + s, p.dbg);
+            tc_fence_after();
+            const float alpha = need ? fast_exp2(m - m_new) : 1.0f;
+            if (need) m = m_new;
+            l *= alpha;
+            uint32_t ov[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              tmem_ld32(tO + c * 32, ov);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st32(tO + c * 32, ov);
+            }
+            tc_wait_st();
+          }
+        }
+
+        // P = exp2(S*scale - m), row sum, pack to 16 bit, store to TMEM
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = c * 64 + 2 * i;
+            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[col >> 5][col & 31]), sc, -m));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[(col + 1) >> 5][(col + 1) & 31]), sc, -m));
+            l += p0 + p1;
+            pk[i] = pack2<kBF16>(p0, p1);
+          }
+          tmem_st32(tP + c * 32, pk);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_p);
+      }
+
+      // epilogue: wait for the last PV, normalise, store
+      mbar_wait(bar_o, (od + w.total - 1) & 1, 0x320 + s, p.dbg);
+      tc_fence_after();
+      od += w.total;
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tmem_ld32(tO + c * 32, ov);
+        tc_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 v4;
+            v4.x = pack2<kBF16>(__uint_as_float(ov[8 * i + 0]) * inv, __uint_as_float(ov[8 * i + 1]) * inv);
+            v4.y = pack2<kBF16>(__uint_as_float(ov[8 * i + 2]) * inv, __uint_as_float(ov[8 * i + 3]) * inv);
+            v4.z = pack2<kBF16>(__uint_as_float(ov[8 * i + 4]) * inv, __uint_as_float(ov[8 * i + 5]) * inv);
+            v4.w = pack2<kBF16>(__uint_as_float(ov[8 * i + 6]) * inv, __uint_as_float(ov[8 * i + 7]) * inv);
+            optr[c * 4 + i] = v4;
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+static int encode_2d(CUtensorMap* tm, int dtype, const void* base, int64_t rows, int64_t cols, int64_t ld_elems,
+                     uint32_t box_rows) {
+  PFN_encodeTiled fn = get_encode_tiled();
+  if (!fn) return set_error(CSA_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
+  cuuint32_t box[2] = {kHD, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, dtype == CSA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(static_cast<int>(r), "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace csa
+
+using namespace csa;
+
+extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
+  if (!a) return set_error(CSA_E_BADARG, "csa_attn_fwd: null args");
+  if (a->struct_size != sizeof(csa_attn_args_t))
+    return set_error(CSA_E_BADARG, "csa_attn_fwd: struct_size %u != %zu (ABI mismatch)", a->struct_size,
+                     sizeof(csa_attn_args_t));
+  if (a->head_dim != CSA_HEAD_DIM) return set_error(CSA_E_SHAPE, "csa_attn_fwd: head_dim %d != 64", a->head_dim);
+  if (a->dtype != CSA_DTYPE_F16 && a->dtype != CSA_DTYPE_BF16)
+    return set_error(CSA_E_BADARG, "csa_attn_fwd: dtype %d", a->dtype);
+  if (a->heads <= 0 || a->n_groups <= 0 || a->n_frames <= 0 || a->n_q <= 0)
+    return set_error(CSA_E_BADARG, "csa_attn_fwd: non-positive geometry");
+  if (!a->q || !a->o) return set_error(CSA_E_BADARG, "csa_attn_fwd: null q/o");
+  const bool use_g = a->list_base >= 0;
+  const bool use_a = use_g || a->ca_len > 0;
+  const bool use_b = a->cb_len > 0;
+  if (!use_a && !use_b) return set_error(CSA_E_BADARG, "csa_attn_fwd: no key segment enabled");
+  if (use_a && (!a->k_a || !a->v_a)) return set_error(CSA_E_BADARG, "csa_attn_fwd: null k_a/v_a");
+  if (use_b && (!a->k_b || !a->v_b)) return set_error(CSA_E_BADARG, "csa_attn_fwd: null k_b/v_b");
+  if (use_g && (!a->idx || !a->counts || (a->idx_stride & 3) || !aligned16(a->idx)))
+    return set_error(CSA_E_BADARG, "csa_attn_fwd: idx/counts null or idx not 16-byte aligned / stride %% 4");
+  const int64_t cols = static_cast<int64_t>(a->heads) * CSA_HEAD_DIM;
+  auto ld_ok = [&](int64_t ld) { return ld >= cols && (ld % 8) == 0; };
+  if (!ld_ok(a->q_ld) || !ld_ok(a->o_ld) || (use_a && !ld_ok(a->a_ld)) || (use_b && !ld_ok(a->b_ld)))
+    return set_error(CSA_E_SHAPE, "csa_attn_fwd: row strides must be >= heads*64 and multiples of 8 elements");
+  if (!aligned16(a->q) || !aligned16(a->o) || (use_a && (!aligned16(a->k_a) || !aligned16(a->v_a))) ||
+      (use_b && (!aligned16(a->k_b) || !aligned16(a->v_b))))
+    return set_error(CSA_E_BADARG, "csa_attn_fwd: pointers must be 16-byte aligned");
+  if (a->ca_len < 0 || a->cb_len < 0) return set_error(CSA_E_BADARG, "csa_attn_fwd: negative segment length");
+
+  AttnKernelParams p;
+  memset(&p, 0, sizeof(p));
+  const int64_t q_rows = static_cast<int64_t>(a->n_groups) * a->n_frames * a->n_q;
+  int rc;
+  if ((rc = encode_2d(&p.tm_q, a->dtype, a->q, q_rows, cols, a->q_ld, kBM))) return rc;
+  // Unused sources still need valid descriptors (they are prefetched); alias them to whatever is present.
+  const void* ka = use_a ? a->k_a : a->k_b;
+  const void* va = use_a ? a->v_a : a->v_b;
+  const int64_t a_ld = use_a ? a->a_ld : a->b_ld;
+  const int64_t a_rows = use_a ? a->a_rows : a->b_rows;
+  const void* kb = use_b ? a->k_b : ka;
+  const void* vb = use_b ? a->v_b : va;
+  const int64_t b_ld = use_b ? a->b_ld : a_ld;
+  const int64_t b_rows = use_b ? a->b_rows : a_rows;
+  if (a_rows <= 0 || b_rows <= 0) return set_error(CSA_E_BADARG, "csa_attn_fwd: a_rows/b_rows must be positive");
+  if ((rc = encode_2d(&p.tm_ka, a->dtype, ka, a_rows, cols, a_ld, kBN))) return rc;
+  if ((rc = encode_2d(&p.tm_va, a->dtype, va, a_rows, cols, a_ld, kBN))) return rc;
+  if ((rc = encode_2d(&p.tm_kag, a->dtype, ka, a_rows, cols, a_ld, 1))) return rc;
+  if ((rc = encode_2d(&p.tm_vag, a->dtype, va, a_rows, cols, a_ld, 1))) return rc;
+  if ((rc = encode_2d(&p.tm_kb, a->dtype, kb, b_rows, cols, b_ld, kBN))) return rc;
+  if ((rc = encode_2d(&p.tm_vb, a->dtype, vb, b_rows, cols, b_ld, kBN))) return rc;
+
+  p.o = a->o;
+  p.o_ld = a->o_ld;
+  p.idx = a->idx;
+  p.counts = a->counts;
+  p.idx_stride = a->idx_stride;
+  p.heads = a->heads;
+  p.n_groups = a->n_groups;
+  p.n_frames = a->n_frames;
+  p.n_q = a->n_q;
+  p.n_qpairs = (a->n_q + 2 * kBM - 1) / (2 * kBM);
+  p.n_units = a->n_groups * a->n_frames * a->heads * p.n_qpairs;
+  p.a_group_rows = a->a_group_rows;
+  p.b_group_rows = a->b_group_rows;
+  p.list_base = use_g ? a->list_base : -1;
+  p.list_step = a->list_step;
+  p.g_adjust = a->g_adjust;
+  p.ca_start = a->ca_start;
+  p.ca_step = a->ca_step;
+  p.ca_len = a->ca_len;
+  p.cb_start = a->cb_start;
+  p.cb_step = a->cb_step;
+  p.cb_len = a->cb_len;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.dbg = debug_record_devptr();
+
+  int dev = 0;
+  cudaError_t ce = cudaGetDevice(&dev);
+  if (ce != cudaSuccess) return set_error(static_cast<int>(ce), "cudaGetDevice: %s", cudaGetErrorString(ce));
+  const int sms = sm_count(dev);
+  if (sms <= 0) return set_error(CSA_E_DEVICE, "csa_attn_fwd: device %d is not sm_100", dev);
+  int grid = p.n_units < sms ? p.n_units : sms;
+  if (a->max_ctas > 0 && grid > a->max_ctas) grid = a->max_ctas;
+
+  const size_t smem = sizeof(AttnSmem) + 1024;
+  auto kern = a->dtype == CSA_DTYPE_BF16 ? csa_attn_kernel<true> : csa_attn_kernel<false>;
+  ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (ce != cudaSuccess)
+    return set_error(static_cast<int>(ce), "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(ce));
+  kern<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) return set_error(static_cast<int>(ce), "csa_attn_kernel launch: %s", cudaGetErrorString(ce));
+  return 0;
+}

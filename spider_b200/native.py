@@ -1,0 +1,279 @@
+"""ctypes binding of ``libcsa_b200.so`` (the C ABI declared in ``include/csa_b200.h``).
+
+The library is the product's only compute path for the consistent-self-attention hot path: there is no CPU or
+PyTorch fallback.  If the shared object is missing or the device is not an sm_100 part, calls raise
+``CsaNativeError`` loudly instead of degrading.
+
+PyTorch is used here only for device memory (``tensor.data_ptr()``) and for the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint8, c_uint32, c_void_p
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcsa_b200.so")
+
+CSA_ABI_VERSION = 1
+CSA_DTYPE_F16 = 0
+CSA_DTYPE_BF16 = 1
+CSA_TILE = 128
+CSA_HEAD_DIM = 64
+
+# every symbol include/csa_b200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "csa_abi_version",
+    "csa_last_error",
+    "csa_device_supported",
+    "csa_debug_stuck",
+    "csa_compact_rows",
+    "csa_validate_mask",
+    "csa_gather_rows",
+    "csa_attn_fwd",
+)
+
+
+class CsaNativeError(RuntimeError):
+    """Raised when libcsa_b200.so is missing, mismatched, or a call into it fails."""
+
+
+class CsaAttnArgs(ctypes.Structure):
+    """Mirror of ``csa_attn_args_t`` (include/csa_b200.h) — field order and types must match exactly."""
+
+    _fields_ = [
+        ("struct_size", c_uint32),
+        ("dtype", c_int32),
+        ("head_dim", c_int32),
+        ("heads", c_int32),
+        ("n_groups", c_int32),
+        ("n_frames", c_int32),
+        ("n_q", c_int32),
+        ("scale", c_float),
+        ("q", c_void_p),
+        ("o", c_void_p),
+        ("q_ld", c_int64),
+        ("o_ld", c_int64),
+        ("k_a", c_void_p),
+        ("v_a", c_void_p),
+        ("a_ld", c_int64),
+        ("a_rows", c_int64),
+        ("a_group_rows", c_int32),
+        ("_pad0", c_int32),
+        ("k_b", c_void_p),
+        ("v_b", c_void_p),
+        ("b_ld", c_int64),
+        ("b_rows", c_int64),
+        ("b_group_rows", c_int32),
+        ("_pad1", c_int32),
+        ("idx", c_void_p),
+        ("counts", c_void_p),
+        ("idx_stride", c_int64),
+        ("list_base", c_int32),
+        ("list_step", c_int32),
+        ("g_adjust", c_int32),
+        ("ca_start", c_int32),
+        ("ca_step", c_int32),
+        ("ca_len", c_int32),
+        ("cb_start", c_int32),
+        ("cb_step", c_int32),
+        ("cb_len", c_int32),
+        ("max_ctas", c_int32),
+        ("flags", c_int32),
+    ]
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library once and declare the prototypes.  Never falls back to anything else."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CsaNativeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C spider_b200/csrc`).  There is no CPU fallback for this path."
+        )
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover - depends on the box
+        raise CsaNativeError(f"cannot load {LIB_PATH}: {e}") from e
+
+    lib.csa_abi_version.restype = c_int32
+    lib.csa_abi_version.argtypes = []
+    lib.csa_last_error.restype = c_char_p
+    lib.csa_last_error.argtypes = []
+    lib.csa_device_supported.restype = c_int32
+    lib.csa_device_supported.argtypes = [c_int32]
+    lib.csa_debug_stuck.restype = c_int32
+    lib.csa_debug_stuck.argtypes = [POINTER(c_uint32)]
+    lib.csa_compact_rows.restype = c_int32
+    lib.csa_compact_rows.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64,
+                                     c_void_p, c_void_p]
+    lib.csa_validate_mask.restype = c_int32
+    lib.csa_validate_mask.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+    lib.csa_gather_rows.restype = c_int32
+    lib.csa_gather_rows.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                    c_int64, c_int32, c_void_p]
+    lib.csa_attn_fwd.restype = c_int32
+    lib.csa_attn_fwd.argtypes = [POINTER(CsaAttnArgs), c_void_p]
+
+    v = lib.csa_abi_version()
+    if v != CSA_ABI_VERSION:
+        raise CsaNativeError(f"libcsa_b200.so ABI version {v} != expected {CSA_ABI_VERSION}; rebuild the library")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().csa_last_error().decode("utf-8", "replace")
+        raise CsaNativeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def _stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise CsaNativeError(
+                "consistent self-attention needs CUDA tensors on a B200; got a CPU tensor and there is no CPU "
+                "fallback in the product path")
+
+
+_checked_devices: set = set()
+
+
+def ensure_device(device: torch.device) -> None:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _checked_devices:
+        return
+    _check(load().csa_device_supported(idx), "csa_device_supported")
+    _checked_devices.add(idx)
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.bfloat16:
+        return CSA_DTYPE_BF16
+    if dt == torch.float16:
+        return CSA_DTYPE_F16
+    raise CsaNativeError(f"consistent self-attention kernels support fp16/bf16 only, got {dt}")
+
+
+def idx_stride_for(n_cols: int) -> int:
+    return (n_cols + CSA_TILE - 1) // CSA_TILE * CSA_TILE
+
+
+def compact_rows(mask_rows: torch.Tensor, n_rows: int, n_cols: int, row_stride: int, block_n: int = 0,
+                 limit_cols: int = 0, idx: Optional[torch.Tensor] = None,
+                 counts: Optional[torch.Tensor] = None):
+    """Compact boolean rows into ascending int32 index lists (see csa_compact_rows).
+
+    ``mask_rows`` is a bool/uint8 CUDA tensor whose first element is row 0, column 0; rows are ``row_stride``
+    bytes apart (0 = the same vector for every row).  Returns ``(idx [n_rows, stride] int32, counts [n_rows])``.
+    """
+    _require_cuda(mask_rows)
+    ensure_device(mask_rows.device)
+    if mask_rows.dtype not in (torch.bool, torch.uint8):
+        raise CsaNativeError(f"mask must be bool/uint8, got {mask_rows.dtype}")
+    stride = idx_stride_for(n_cols)
+    if idx is None:
+        idx = torch.empty((n_rows, stride), dtype=torch.int32, device=mask_rows.device)
+    if counts is None:
+        counts = torch.empty((n_rows,), dtype=torch.int32, device=mask_rows.device)
+    rc = load().csa_compact_rows(mask_rows.data_ptr(), row_stride, n_rows, n_cols, block_n, limit_cols,
+                                 idx.data_ptr(), idx.stride(0), counts.data_ptr(), _stream_ptr(mask_rows))
+    _check(rc, "csa_compact_rows")
+    return idx, counts
+
+
+def validate_mask(mask: torch.Tensor, block_n: int) -> torch.Tensor:
+    """Returns a device int32 scalar: number of 16-byte words that differ from their block's first row."""
+    _require_cuda(mask)
+    ensure_device(mask.device)
+    if mask.dim() != 2 or mask.stride(1) != 1:
+        raise CsaNativeError("validate_mask expects a 2-D mask with unit column stride")
+    n_bad = torch.zeros((1,), dtype=torch.int32, device=mask.device)
+    rc = load().csa_validate_mask(mask.data_ptr(), mask.stride(0), mask.shape[0], mask.shape[1], block_n,
+                                  n_bad.data_ptr(), _stream_ptr(mask))
+    _check(rc, "csa_validate_mask")
+    return n_bad
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, max_rows: int, row_base: int = 0,
+                count: Optional[torch.Tensor] = None, count_adjust: int = 0,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i] = src[row_base + idx[i]] for i < min(count + adjust, max_rows).  src is 2-D, rows contiguous."""
+    _require_cuda(src, idx)
+    ensure_device(src.device)
+    if src.dim() != 2 or src.stride(1) != 1:
+        raise CsaNativeError("gather_rows expects a 2-D source with unit column stride")
+    es = src.element_size()
+    if out is None:
+        out = torch.empty((max_rows, src.shape[1]), dtype=src.dtype, device=src.device)
+    rc = load().csa_gather_rows(src.data_ptr(), src.stride(0) * es, row_base, idx.data_ptr(),
+                                count.data_ptr() if count is not None else None, count_adjust, max_rows,
+                                out.data_ptr(), out.stride(0) * es, src.shape[1] * es, _stream_ptr(src))
+    _check(rc, "csa_gather_rows")
+    return out
+
+
+def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_frames: int, n_q: int,
+             k_a: Optional[torch.Tensor] = None, v_a: Optional[torch.Tensor] = None, a_group_rows: int = 0,
+             k_b: Optional[torch.Tensor] = None, v_b: Optional[torch.Tensor] = None, b_group_rows: int = 0,
+             idx: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
+             list_base: int = -1, list_step: int = 0, g_adjust: int = 0,
+             ca: tuple = (0, 0, 0), cb: tuple = (0, 0, 0), scale: Optional[float] = None,
+             max_ctas: int = 0) -> torch.Tensor:
+    """Launch csa_attn_fwd on the current stream.  All matrices are 2-D ``(rows, heads*64)`` with unit column stride."""
+    _require_cuda(q, o)
+    ensure_device(q.device)
+    for t in (q, o, k_a, v_a, k_b, v_b):
+        if t is not None and (t.dim() != 2 or t.stride(1) != 1):
+            raise CsaNativeError("attn_fwd expects 2-D (rows, heads*64) tensors with unit column stride")
+    a = CsaAttnArgs()
+    a.struct_size = ctypes.sizeof(CsaAttnArgs)
+    a.dtype = dtype_code(q.dtype)
+    a.head_dim = CSA_HEAD_DIM
+    a.heads = heads
+    a.n_groups = n_groups
+    a.n_frames = n_frames
+    a.n_q = n_q
+    a.scale = float(scale) if scale is not None else CSA_HEAD_DIM ** -0.5
+    a.q = q.data_ptr()
+    a.o = o.data_ptr()
+    a.q_ld = q.stride(0)
+    a.o_ld = o.stride(0)
+    if k_a is not None:
+        if v_a is None or v_a.stride(0) != k_a.stride(0) or v_a.shape != k_a.shape or k_a.dtype != q.dtype:
+            raise CsaNativeError("k_a and v_a must have the same shape, row stride and the dtype of q")
+        a.k_a, a.v_a = k_a.data_ptr(), v_a.data_ptr()
+        a.a_ld, a.a_rows, a.a_group_rows = k_a.stride(0), k_a.shape[0], a_group_rows
+    if k_b is not None:
+        if v_b is None or v_b.stride(0) != k_b.stride(0) or v_b.shape != k_b.shape or k_b.dtype != q.dtype:
+            raise CsaNativeError("k_b and v_b must have the same shape, row stride and the dtype of q")
+        a.k_b, a.v_b = k_b.data_ptr(), v_b.data_ptr()
+        a.b_ld, a.b_rows, a.b_group_rows = k_b.stride(0), k_b.shape[0], b_group_rows
+    if idx is not None:
+        a.idx, a.counts, a.idx_stride = idx.data_ptr(), counts.data_ptr(), idx.stride(0)
+    a.list_base, a.list_step, a.g_adjust = list_base, list_step, g_adjust
+    a.ca_start, a.ca_step, a.ca_len = ca
+    a.cb_start, a.cb_step, a.cb_len = cb
+    a.max_ctas = max_ctas
+    a.flags = 0
+    _check(load().csa_attn_fwd(ctypes.byref(a), _stream_ptr(q)), "csa_attn_fwd")
+    return o
+
+
+def debug_stuck():
+    out = (c_uint32 * 4)()
+    if load().csa_debug_stuck(out):
+        return tuple(out)
+    return None
