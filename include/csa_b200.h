@@ -72,7 +72,8 @@ int csa_compact_rows(const uint8_t* mask, int64_t row_stride, int32_t n_rows, in
 /*
  * Check that a dense (n_rows x n_cols) bool mask, row stride `row_stride` bytes, consists of blocks of `block_n`
  * identical consecutive rows.  *n_bad (device int32, must be zeroed by the caller) receives the number of 16-byte
- * words that differ from the first row of their block.  HBM-bound: reads the mask once.
+ * words (bytes, when base or stride is not 16-byte aligned) that differ from the first row of their block.
+ * HBM-bound: reads the mask once.
  */
 int csa_validate_mask(const uint8_t* mask, int64_t row_stride, int32_t n_rows, int32_t n_cols, int32_t block_n,
                       int32_t* n_bad, void* stream);

@@ -4,3 +4,7 @@ Only what the hot path needs: ``csrc/`` (sm_100a CUDA kernels + the C ABI of ``i
 host-side mirror of the reference's diffusers attention-processor interface.
 """
 __version__ = "0.1.0"
+
+from .install import install, make_processor_class, set_attention_processor, uninstall  # noqa: E402,F401
+from .masks import CompactMask, cal_attn_mask_xl  # noqa: E402,F401
+from .processor import GLOBALS, SpatialAttnProcessor2_0, StoryGlobals  # noqa: E402,F401

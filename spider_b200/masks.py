@@ -1,0 +1,115 @@
+"""Sampling masks of Consistent Self-Attention in compact form.
+
+The reference builds a dense ``(T*N, T*N)`` boolean mask per resolution every denoise step
+(``cal_attn_mask_xl``, StoryDiffusion/utils/gradio_utils.py:241-287; 419 MB at 1024², quadratic in frames) although
+it is fully determined by ONE sampled vector ``r`` of ``T*N`` booleans: row block ``i`` is
+``(r & col < F*N) | col in block_i``.  ``CompactMask`` keeps ``r`` only and turns it into per-frame ascending key
+index lists with the ``csa_compact_rows`` CUDA kernel (bit-exact w.r.t. ``torch.nonzero(mask[i*N])``).
+
+RNG parity: ``cal_attn_mask_xl`` below consumes the default generator of ``device`` exactly like the reference —
+two ``torch.rand`` calls of shapes ``(1, T*n32)`` then ``(1, T*n16)`` in ``dtype`` (gradio_utils.py:257-258) — so a
+pipeline seeded like the reference (Comic_Generation.py:35-40) sees the same sample vectors.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import native
+
+
+class CompactMask:
+    """One resolution's sampling mask: the T distinct rows as index lists, built lazily on the device.
+
+    ``lists()`` returns ``(idx [T, stride] int32, counts [T] int32)``: row ``f < F`` is the key list of write-mode
+    frame ``f`` (columns < F*N), row ``F`` is the read-mode list (sampled bank rows followed by the own block
+    ``[F*N, T*N)``, whose N entries the attention kernel drops via ``g_adjust = -N``).
+    """
+
+    def __init__(self, total_length: int, id_length: int, n_tokens: int, sample: Optional[torch.Tensor] = None,
+                 dense: Optional[torch.Tensor] = None):
+        if (sample is None) == (dense is None):
+            raise ValueError("CompactMask needs exactly one of `sample` (T*N bool vector) or `dense` ((T*N)^2 mask)")
+        self.total_length = int(total_length)
+        self.id_length = int(id_length)
+        self.n_tokens = int(n_tokens)
+        self._sample = sample
+        self._dense = dense
+        self._lists: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+
+    # what the reference's mask tensor exposes and drivers may look at
+    @property
+    def shape(self):
+        s = self.total_length * self.n_tokens
+        return torch.Size((s, s))
+
+    @property
+    def device(self):
+        return (self._sample if self._sample is not None else self._dense).device
+
+    def lists(self, device=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Index lists on ``device`` (default: where the sample lives).  A sample drawn on another device — e.g.
+        ``device="cpu"`` processors, whose torch.rand calls consume the CPU generator — is moved once."""
+        if self._lists is None:
+            T, F, N = self.total_length, self.id_length, self.n_tokens
+            if device is not None:
+                if self._sample is not None and self._sample.device != torch.device(device):
+                    self._sample = self._sample.to(device)
+                if self._dense is not None and self._dense.device != torch.device(device):
+                    self._dense = self._dense.to(device)
+            if self._sample is not None:
+                r = self._sample
+                if r.dtype != torch.bool or r.numel() != T * N or not r.is_contiguous():
+                    raise ValueError("sample vector must be a contiguous bool tensor of T*N elements")
+                self._lists = native.compact_rows(r, T, T * N, 0, block_n=N, limit_cols=F * N)
+            else:
+                m = self._dense
+                # the T distinct rows are rows 0, N, 2N, ... of the dense mask (gradio_utils.py:285-286)
+                self._lists = native.compact_rows(m, T, T * N, N * m.stride(0))
+        return self._lists
+
+    def dense(self) -> torch.Tensor:
+        """Materialise the reference's dense mask (debugging / interoperability only; O((T*N)^2) bytes)."""
+        if self._dense is not None:
+            return self._dense
+        T, F, N = self.total_length, self.id_length, self.n_tokens
+        rows = self._sample.unsqueeze(0).repeat(T, 1)
+        rows[:, F * N:] = False
+        for i in range(T):
+            rows[i, i * N:(i + 1) * N] = True
+        return rows.unsqueeze(1).repeat(1, N, 1).reshape(-1, T * N)
+
+
+def cal_attn_mask_xl(total_length, id_length, sa32, sa64, height, width, device="cuda", dtype=torch.float16):
+    """Drop-in for the reference's ``cal_attn_mask_xl`` (same signature, same RNG consumption) that returns two
+    ``CompactMask`` objects instead of two dense tensors."""
+    n32 = (height // 32) * (width // 32)   # gradio_utils.py:250
+    n16 = (height // 16) * (width // 16)   # gradio_utils.py:251
+    r32 = torch.rand((1, total_length * n32), device=device, dtype=dtype) < sa32   # :257
+    r16 = torch.rand((1, total_length * n16), device=device, dtype=dtype) < sa64   # :258
+    return (CompactMask(total_length, id_length, n32, sample=r32[0]),
+            CompactMask(total_length, id_length, n16, sample=r16[0]))
+
+
+def from_dense(mask: torch.Tensor, total_length: int, id_length: int, validate: bool = True) -> CompactMask:
+    """Wrap a dense mask produced by the unmodified reference sampler (Comic_Generation.py:376).
+
+    With ``validate`` the premise of the compaction — all N rows of a frame block are identical — is checked on the
+    device (HBM-bound pass over the mask, one host sync); a mask that violates it raises ``ValueError`` instead of
+    being silently mis-compacted.
+    """
+    if mask.dim() != 2 or mask.shape[0] != mask.shape[1] or mask.dtype != torch.bool:
+        raise ValueError(f"expected a square 2-D bool mask, got {tuple(mask.shape)} {mask.dtype}")
+    if mask.shape[0] % total_length:
+        raise ValueError(f"mask side {mask.shape[0]} is not a multiple of total_length {total_length}")
+    if mask.stride(1) != 1:
+        mask = mask.contiguous()
+    n = mask.shape[0] // total_length
+    if validate:
+        bad = int(native.validate_mask(mask, n).item())
+        if bad:
+            raise ValueError(
+                f"attention mask has {bad} 16-byte words that differ between rows of one frame block; consistent "
+                "self-attention kernels need the per-frame mask structure of cal_attn_mask_xl")
+    return CompactMask(total_length, id_length, n, dense=mask)

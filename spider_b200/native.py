@@ -88,6 +88,16 @@ class CsaAttnArgs(ctypes.Structure):
 
 _lib: Optional[ctypes.CDLL] = None
 
+# Launch accounting (how many of OUR kernels were launched, by entry point) and optional CUDA-event timing of the
+# attention launches on the launching stream; both are read by bench.py.
+LAUNCHES = {"csa_attn_fwd": 0, "csa_compact_rows": 0, "csa_validate_mask": 0, "csa_gather_rows": 0}
+ATTN_EVENTS: Optional[list] = None   # when a list: (start_event, end_event, n_groups, n_frames, n_q, heads) appended
+
+
+def reset_launch_counters() -> None:
+    for k in LAUNCHES:
+        LAUNCHES[k] = 0
+
 
 def load() -> ctypes.CDLL:
     """Load the shared library once and declare the prototypes.  Never falls back to anything else."""
@@ -191,6 +201,7 @@ def compact_rows(mask_rows: torch.Tensor, n_rows: int, n_cols: int, row_stride: 
     rc = load().csa_compact_rows(mask_rows.data_ptr(), row_stride, n_rows, n_cols, block_n, limit_cols,
                                  idx.data_ptr(), idx.stride(0), counts.data_ptr(), _stream_ptr(mask_rows))
     _check(rc, "csa_compact_rows")
+    LAUNCHES["csa_compact_rows"] += 1
     return idx, counts
 
 
@@ -204,6 +215,7 @@ def validate_mask(mask: torch.Tensor, block_n: int) -> torch.Tensor:
     rc = load().csa_validate_mask(mask.data_ptr(), mask.stride(0), mask.shape[0], mask.shape[1], block_n,
                                   n_bad.data_ptr(), _stream_ptr(mask))
     _check(rc, "csa_validate_mask")
+    LAUNCHES["csa_validate_mask"] += 1
     return n_bad
 
 
@@ -222,6 +234,7 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, max_rows: int, row_base: i
                                 count.data_ptr() if count is not None else None, count_adjust, max_rows,
                                 out.data_ptr(), out.stride(0) * es, src.shape[1] * es, _stream_ptr(src))
     _check(rc, "csa_gather_rows")
+    LAUNCHES["csa_gather_rows"] += 1
     return out
 
 
@@ -268,7 +281,16 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
     a.cb_start, a.cb_step, a.cb_len = cb
     a.max_ctas = max_ctas
     a.flags = 0
-    _check(load().csa_attn_fwd(ctypes.byref(a), _stream_ptr(q)), "csa_attn_fwd")
+    if ATTN_EVENTS is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _check(load().csa_attn_fwd(ctypes.byref(a), _stream_ptr(q)), "csa_attn_fwd")
+        e1.record()
+        ATTN_EVENTS.append((e0, e1, n_groups, n_frames, n_q, heads))
+    else:
+        _check(load().csa_attn_fwd(ctypes.byref(a), _stream_ptr(q)), "csa_attn_fwd")
+    LAUNCHES["csa_attn_fwd"] += 1
     return o
 
 

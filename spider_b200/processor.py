@@ -1,0 +1,271 @@
+"""Drop-in ``SpatialAttnProcessor2_0`` — the diffusers attention-processor plugin of StoryDiffusion's Consistent
+Self-Attention, re-implemented on top of ``libcsa_b200.so`` (hand-written sm_100a kernels).
+
+Mirrors the reference class (StoryDiffusion/Comic_Generation.py:46-268; identical copies in app.py:66-294,
+predict.py:135-409): same constructor and ``__call__(attn, hidden_states, encoder_hidden_states, attention_mask,
+temb)`` signature, same public attributes (``id_bank, id_length, total_length, device, dtype``), same control
+surface — the module globals ``write, cur_step, attn_count, total_count, sa32, sa64, height, width, mask1024,
+mask4096`` of the *host* module (:82-85) — same branch logic and the same consumption of Python's ``random`` and of
+torch's generator, so a pipeline seeded like the reference walks through the same gates and sample vectors.
+
+What changes is how the attention is computed:
+  * the dense ``(T*N)^2`` mask is never used as a mask: its T distinct rows are compacted once per step into key
+    index lists (``CompactMask``), and regenerated masks are sampled directly in compact form;
+  * ``F.scaled_dot_product_attention(q, k, v, attn_mask=...)`` (:175-177, :248-250) becomes one launch of the
+    tcgen05/TMEM flash-attention kernel over TMA-gathered keys (``native.attn_fwd``);
+  * the ``torch.cat`` of bank and current frames (:92) and the re-projection of the bank rows (:162-165) disappear:
+    the write pass keeps the projected K/V it computes anyway (``bank.py``) and the kernel reads bank and current
+    K/V in place as two sources.
+The four ``nn.Linear`` projections stay with the ``attn`` module that owns the weights (cuBLAS).
+
+There is no CPU / eager fallback: non-CUDA tensors, non 16-bit dtypes or a missing library raise.
+"""
+from __future__ import annotations
+
+import random
+from typing import Optional
+
+import torch
+import torch.nn.functional as F_torch
+
+from . import masks as _masks
+from . import native
+from .bank import STORE_MODES, BankEntry, IdBank
+
+
+class StoryGlobals:
+    """Default host namespace: the reference's module globals (Comic_Generation.py:82-85, :327-349) as attributes.
+    ``install()`` binds processors to the reference's own module instead."""
+
+    def __init__(self):
+        self.write = False
+        self.cur_step = 0
+        self.attn_count = 0
+        self.total_count = 0
+        self.sa32 = 0.5
+        self.sa64 = 0.5
+        self.height = 768
+        self.width = 768
+        self.id_length = 4
+        self.total_length = 5
+        self.mask1024 = None
+        self.mask4096 = None
+
+
+GLOBALS = StoryGlobals()
+
+
+class SpatialAttnProcessor2_0(torch.nn.Module):
+    r"""Consistent Self-Attention processor (B200-native).  See the module docstring.
+
+    Class attributes that configure every instance (set them on the class, or on a bound subclass returned by
+    ``install.make_processor_class``):
+      _host            namespace holding the control globals (a module or any object with those attributes)
+      bank_store       "kv" | "hidden" | "both"  — what the write pass keeps per step (``bank.py``)
+      validate_masks   check dense masks supplied from outside for the per-frame structure (one sync per mask)
+    """
+
+    _host = GLOBALS
+    bank_store = "kv"
+    validate_masks = True
+
+    def __init__(self, hidden_size=None, cross_attention_dim=None, id_length=4, device="cuda", dtype=torch.float16):
+        super().__init__()
+        if not hasattr(F_torch, "scaled_dot_product_attention"):   # Comic_Generation.py:64-65
+            raise ImportError("AttnProcessor2_0 requires PyTorch 2.0, to use it, please upgrade PyTorch to 2.0.")
+        self.device = device
+        self.dtype = dtype
+        self.hidden_size = hidden_size
+        self.cross_attention_dim = cross_attention_dim
+        self.total_length = id_length + 1
+        self.id_length = id_length
+        self.id_bank = IdBank()
+        self.dist = None   # optional frame sharding across GPUs (spider_b200.dist.FrameSharding)
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def _compact_mask(self, h, n_tokens: int) -> _masks.CompactMask:
+        """mask1024 / mask4096 selection of Comic_Generation.py:105-114, returned in compact form."""
+        use32 = n_tokens == (h.height // 32) * (h.width // 32)
+        m = h.mask1024 if use32 else h.mask4096
+        if isinstance(m, _masks.CompactMask):
+            cm = m
+        elif isinstance(m, torch.Tensor):
+            # dense mask from the unmodified driver (Comic_Generation.py:376): compact it once, reuse it for every
+            # layer of the step (the processors of all layers share the host's mask tensors)
+            cache = getattr(h, "_csa_dense_cache", None)
+            if cache is None:
+                cache = {}
+                setattr(h, "_csa_dense_cache", cache)
+            key = (m.data_ptr(), m._version, tuple(m.shape))
+            hit = cache.get(use32)
+            if hit is not None and hit[0] == key:
+                cm = hit[1]
+            else:
+                if not m.is_cuda:   # e.g. a driver that sampled on the CPU generator: move once, compact on GPU
+                    m = m.to(self._last_device)
+                cm = _masks.from_dense(m, self.total_length, self.id_length, validate=self.validate_masks)
+                cache[use32] = (key, cm)
+        else:
+            raise TypeError(f"mask1024/mask4096 must be a torch.Tensor or CompactMask, got {type(m)}")
+        if cm.total_length != self.total_length or cm.id_length != self.id_length:
+            raise ValueError(
+                f"mask was sampled for total_length={cm.total_length}, id_length={cm.id_length} but the processor "
+                f"has total_length={self.total_length}, id_length={self.id_length}")
+        if cm.n_tokens != n_tokens:
+            raise ValueError(
+                f"mask holds {cm.n_tokens} tokens per frame but hidden_states has {n_tokens} "
+                "(height/width globals do not match the latent size)")
+        return cm
+
+    @staticmethod
+    def _check_input(x: torch.Tensor) -> None:
+        if not x.is_cuda:
+            raise native.CsaNativeError(
+                "SpatialAttnProcessor2_0 (B200) got CPU hidden_states: this path has no CPU fallback")
+        if x.dtype not in (torch.float16, torch.bfloat16):
+            raise native.CsaNativeError(
+                f"SpatialAttnProcessor2_0 (B200) computes in fp16/bf16; got {x.dtype} — run the pipeline in half "
+                "precision as the reference does (Comic_Generation.py:313)")
+
+    # ------------------------------------------------------------------------------------------------ __call__
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None):
+        h = self._host
+        if attention_mask is not None:
+            raise NotImplementedError("SpatialAttnProcessor2_0 (B200): a caller-supplied attention_mask is not "
+                                      "supported (self-attention layers of SDXL never pass one)")
+        if encoder_hidden_states is not None:
+            raise NotImplementedError("SpatialAttnProcessor2_0 (B200) is a self-attention processor: "
+                                      "encoder_hidden_states must be None (the id_bank provides the extra keys)")
+        self._check_input(hidden_states)
+        self._last_device = hidden_states.device
+
+        residual = hidden_states
+        if attn.spatial_norm is not None:
+            hidden_states = attn.spatial_norm(hidden_states, temb)
+        input_ndim = hidden_states.ndim
+        if input_ndim == 4:
+            b4, c4, h4, w4 = hidden_states.shape
+            hidden_states = hidden_states.view(b4, c4, h4 * w4).transpose(1, 2)
+        if hidden_states.ndim != 3:
+            raise ValueError(f"hidden_states must be (B, N, C) or (B, C, H, W), got {tuple(hidden_states.shape)}")
+        B, N, C = hidden_states.shape
+        heads = attn.heads
+        if C != heads * native.CSA_HEAD_DIM:
+            raise native.CsaNativeError(f"head_dim {C // heads} != 64: not an SDXL self-attention layer")
+        x = hidden_states
+        if attn.group_norm is not None:
+            x = attn.group_norm(x.transpose(1, 2)).transpose(1, 2)
+        x = x.contiguous()
+        Fl = self.id_length
+        write = bool(h.write)
+        cur_step = h.cur_step
+
+        # projections (the reference's to_q/to_k/to_v calls, :155,164-165 / :230,237-238); K/V of the current
+        # input are needed by every branch
+        q = attn.to_q(x).view(B * N, C)
+        k = attn.to_k(x).view(B * N, C)
+        v = attn.to_v(x).view(B * N, C)
+
+        entry: Optional[BankEntry] = None
+        if write:
+            # :87-89 — keep what the read passes need.  K/V are this call's projection outputs (zero-copy).
+            if B < Fl:
+                raise ValueError(f"write pass needs at least id_length={Fl} frames, got batch {B}")
+            keep_hidden = self.bank_store in ("hidden", "both")
+            keep_kv = self.bank_store in ("kv", "both")
+            entry = BankEntry(hidden_states[:Fl] if keep_hidden else None,
+                              hidden_states[Fl:] if keep_hidden else None,
+                              k if keep_kv else None, v if keep_kv else None)
+            self.id_bank[cur_step] = entry
+        else:
+            entry = self.id_bank[cur_step]   # KeyError for a step the write pass never reached (:92)
+            if B != 2:
+                raise ValueError(f"read pass expects batch 2 (uncond, cond), got {B}")
+
+        o = torch.empty_like(q)
+        branch = "early"
+        if cur_step < 5:                                        # :94-96
+            if write:
+                self._attn_standard(q, k, v, o, B, N, heads)
+            else:
+                self._attn_read(attn, entry, q, k, v, o, N, heads, cm=None)
+        else:
+            random_number = random.random()                     # :98 — exactly one draw per call
+            rand_num = 0.3 if cur_step < 20 else 0.1            # :99-102
+            if random_number > rand_num:
+                branch = "consistent"
+                cm = self._compact_mask(h, N)
+                if write:
+                    if B != 2 * Fl:
+                        raise ValueError(f"consistent write pass expects batch 2*id_length={2 * Fl}, got {B} "
+                                         "(the reference fails with a mask shape error here)")
+                    self._attn_write(q, k, v, o, N, heads, cm)
+                else:
+                    self._attn_read(attn, entry, q, k, v, o, N, heads, cm=cm)
+            else:
+                branch = "standard"
+                self._attn_standard(q, k, v, o, B, N, heads)    # :118 — bank ignored even when reading
+        self._last_branch = branch
+
+        out = o.view(B, N, C)
+        out = attn.to_out[0](out)                               # :185 / :256
+        out = attn.to_out[1](out)
+        if input_ndim == 4:
+            out = out.transpose(-1, -2).reshape(b4, c4, h4, w4)
+        if attn.residual_connection:
+            out = out + residual
+        if attn.rescale_output_factor != 1.0:
+            out = out / attn.rescale_output_factor
+
+        h.attn_count += 1                                       # :119-125
+        if h.attn_count == h.total_count:
+            h.attn_count = 0
+            h.cur_step += 1
+            h.mask1024, h.mask4096 = _masks.cal_attn_mask_xl(
+                self.total_length, self.id_length, h.sa32, h.sa64, h.height, h.width,
+                device=self.device, dtype=self.dtype)
+        return out
+
+    # ------------------------------------------------------------------------------------------------ branches
+    def _attn_standard(self, q, k, v, o, B, N, heads):
+        """__call2__ with encoder_hidden_states=None (:198-268): plain per-frame self-attention."""
+        native.attn_fwd(q, o, heads=heads, n_groups=1, n_frames=B, n_q=N,
+                        k_b=k, v_b=v, b_group_rows=B * N, cb=(0, N, N))
+
+    def _attn_write(self, q, k, v, o, N, heads, cm):
+        """__call1__ in write mode (:129-196 with mask[:F*N,:F*N]): frame f attends its own block plus the sampled
+        rows of all identity frames of the same CFG half."""
+        Fl = self.id_length
+        if self.dist is not None:
+            return self.dist.attn_write(q, k, v, o, N, heads, cm, Fl)
+        idx, counts = cm.lists(q.device)
+        native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=Fl, n_q=N,
+                        k_a=k, v_a=v, a_group_rows=Fl * N,
+                        idx=idx, counts=counts, list_base=0, list_step=1)
+
+    def _attn_read(self, attn, entry, q, k, v, o, N, heads, cm):
+        """Read mode: keys = id_bank rows (all of them for early steps, :94-96; the sampled ones for the consistent
+        branch, mask[F*N:], :106-108) + the current frame, per CFG half.  The bank is K/V source A, the current
+        projection source B; nothing is concatenated."""
+        Fl = self.id_length
+        kb, vb = entry.kv(attn, device=q.device)
+        if kb.shape[0] != 2 * Fl * N or kb.shape[1] != q.shape[1]:
+            raise ValueError(f"id_bank entry has K/V of shape {tuple(kb.shape)}, expected {(2 * Fl * N, q.shape[1])}")
+        if kb.dtype != q.dtype:
+            kb, vb = kb.to(q.dtype), vb.to(q.dtype)
+        if cm is None:
+            native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=1, n_q=N,
+                            k_a=kb, v_a=vb, a_group_rows=Fl * N, ca=(0, 0, Fl * N),
+                            k_b=k, v_b=v, b_group_rows=N, cb=(0, 0, N))
+        else:
+            idx, counts = cm.lists(q.device)
+            native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=1, n_q=N,
+                            k_a=kb, v_a=vb, a_group_rows=Fl * N,
+                            idx=idx, counts=counts, list_base=Fl, list_step=0, g_adjust=-N,
+                            k_b=k, v_b=v, b_group_rows=N, cb=(0, 0, N))
+
+
+def set_bank_store(mode: str, cls=SpatialAttnProcessor2_0) -> None:
+    if mode not in STORE_MODES:
+        raise ValueError(f"bank_store must be one of {STORE_MODES}")
+    cls.bank_store = mode
