@@ -1,0 +1,513 @@
+#!/usr/bin/env python
+"""bench.py — Consistent Self-Attention throughput of one SDXL denoise step on B200 (driver contract).
+
+A *step* is one pass of the hot path over one denoise step of a story's WRITE pass: every self-attention layer that
+the reference swaps to ``SpatialAttnProcessor2_0`` (StoryDiffusion/Comic_Generation.py:353-371 — the 36 ``attn1``
+layers of SDXL's up blocks: 30 at (H/32 x W/32) tokens / 1280 ch / 20 heads + 6 at (H/16 x W/16) / 640 ch / 10 heads)
+is called once through the processor's public ``__call__`` with a batch of ``2 * frames`` latents (CFG doubling),
+in the consistent branch (``cur_step = 25``, gate forced open), followed by the per-step mask re-sampling
+(:119-125).  Each call = 3 projections (cuBLAS, owned by the attn module), one launch of the tcgen05 flash-attention
+kernel over the compacted key lists, the output projection; once per step and resolution the sampled mask vector is
+compacted into key index lists.
+
+  metric   attention TFLOP/s = ALGORITHMIC attention FLOPs of the step (4*d*H*2*sum_f N*K_f, K_f read back from the
+           index lists; projections and softmax not counted) / step time.  ``ms_per_step`` is ms per denoise step.
+  value    device-resident inputs, CUDA events around K steps, max over ranks.
+  e2e      same step through the same processor calls, but every layer's latents start in pinned HOST memory and
+           every layer's output is copied back to the host inside the timed region.
+  roofline the attention kernel alone: algorithmic FLOPs / CUDA-event time of the attention launches of the timed
+           region, against the measured dense bf16 peak (MEASURED_PEAKS.json).
+  cpu_baseline / --impl reference
+           the reference algorithm (oracle/reference_port.py, the CPU restatement pinned to the reference by
+           tests/golden) timed on this box's host cores on a bounded sample of the same workload.
+
+N > 1 (torchrun, one rank per GPU): the 2*frames (CFG half, frame) units are sharded over the ranks
+(spider_b200/dist.py); per consistent layer the sampled K/V rows are exchanged inside each CFG group.  Total work is
+fixed, so ``scaling`` is "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+from torch import nn  # noqa: E402
+
+HEAD_DIM = 64
+METRIC = "consistent_self_attn_tflops"
+UNIT = "TFLOP/s"
+
+
+# ------------------------------------------------------------------------------------------------ workload
+class SelfAttnModule(nn.Module):
+    """What diffusers' ``Attention`` exposes to a processor for an SDXL attn1 layer (bias-free q/k/v, biased out,
+    dropout 0, no norms, no residual) — random-init weights, see SURVEY.md §8b for the attribute list."""
+
+    def __init__(self, channels: int, heads: int):
+        super().__init__()
+        self.heads = heads
+        self.to_q = nn.Linear(channels, channels, bias=False)
+        self.to_k = nn.Linear(channels, channels, bias=False)
+        self.to_v = nn.Linear(channels, channels, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(channels, channels, bias=True), nn.Dropout(0.0)])
+        self.spatial_norm = None
+        self.group_norm = None
+        self.norm_cross = None
+        self.residual_connection = False
+        self.rescale_output_factor = 1.0
+        self.eval()
+
+
+def layer_plan(height: int, width: int, placement: str):
+    """[(tokens, channels, heads)] in UNet execution order.  EXTERNAL SDXL-base config."""
+    n32 = (height // 32) * (width // 32)
+    n16 = (height // 16) * (width // 16)
+    plan = []
+    if placement == "all":   # BASELINE config 3: every attn1 layer swapped
+        plan += [(n16, 640, 10)] * 4 + [(n32, 1280, 20)] * 20 + [(n32, 1280, 20)] * 10
+    plan += [(n32, 1280, 20)] * 30 + [(n16, 640, 10)] * 6   # up_blocks.0 / up_blocks.1 (reference placement)
+    return plan
+
+
+def attn_flops(n_q: int, heads: int, key_counts) -> float:
+    """4 * d * H * 2 (CFG halves) * sum_f N * K_f  — QK^T and PV at 2 FLOP/MAC."""
+    return 4.0 * HEAD_DIM * heads * 2 * sum(n_q * int(k) for k in key_counts)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            # "under load" = the upper half of the power samples (the sampler also sees the idle edges)
+            thr = statistics.median(pw)
+            load = [s for s, p_ in zip(sm, pw) if p_ >= thr] or sm
+            out.update(sm_mhz=statistics.median(load), sm_max_mhz=max(mx), power_w_max=max(pw),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference
+def cpu_reference_sample(args, reps: int):
+    """Time the reference algorithm (oracle port, fp32, torch CPU with all host threads) on a bounded sample of the
+    step: ONE write-consistent call of a 32x32-class layer and ONE of a 64x64-class layer, dense (T*N)^2 mask as the
+    reference builds it, extrapolated to the step by the layer counts of the plan.  Returns a dict."""
+    from oracle import reference_port as rp          # the only place bench.py touches oracle/: the CPU baseline
+    from oracle.fake_diffusers import FakeAttention
+
+    Fl = args.frames
+    H = W = args.res
+    plan = layer_plan(H, W, args.placement)
+    kinds = {}
+    for (n, c, h) in plan:
+        kinds[(n, c, h)] = kinds.get((n, c, h), 0) + 1
+    torch.manual_seed(0)
+    random.seed(0)
+    m32, m16 = rp.cal_attn_mask_xl(Fl + 1, Fl, args.sa, args.sa, H, W)
+    n32 = (H // 32) * (W // 32)
+    per_kind = {}
+    for (n, c, h), cnt in kinds.items():
+        attn = FakeAttention(c, h)
+        x = torch.randn(2 * Fl, n, c)
+        st = rp.StoryState(write=True, cur_step=25, total_count=10 ** 9, sa32=args.sa, sa64=args.sa, height=H,
+                           width=W, mask1024=m32, mask4096=m16)
+        orc = rp.ConsistentAttnOracle(st, id_length=Fl)
+        mask = m32 if n == n32 else m16
+        rows = mask[::n][:Fl, :Fl * n]
+        counts = rows.sum(dim=1).tolist()
+        best = float("inf")
+        with torch.no_grad():
+            for _ in range(reps):
+                st.cur_step = 25
+                t0 = time.perf_counter()
+                orc.consistent(attn, x, None, mask[:Fl * n, :Fl * n])
+                best = min(best, time.perf_counter() - t0)
+        per_kind[(n, c, h)] = (best, attn_flops(n, h, counts), cnt)
+    t_step = sum(t * cnt for t, _, cnt in per_kind.values())
+    f_step = sum(f * cnt for _, f, cnt in per_kind.values())
+    t_sample = sum(t for t, _, _ in per_kind.values())
+    return {
+        "value": f_step / t_step / 1e12,
+        "unit": UNIT,
+        "cores": torch.get_num_threads(),
+        "host_cpus": os.cpu_count(),
+        "kind": "port",
+        "sample": (f"one write-consistent call per layer class ({', '.join(f'N={n} C={c}' for n, c, _ in per_kind)}), "
+                   f"fp32, dense mask, best of {reps}; {t_sample:.2f} s per sample; extrapolated to the "
+                   f"{len(plan)}-layer step by layer counts ({t_step:.1f} s/step)"),
+        "ms_per_step": t_step * 1e3,
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    reps = max(1, min(args.steps, 3))
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_sample(args, 1)
+    base = cpu_reference_sample(args, reps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, n_gpus=args.gpus),
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus: int):
+    plan = layer_plan(args.res, args.res, args.placement)
+    return {
+        "workload": (f"SDXL {args.res}x{args.res} story write pass, {args.frames} frames x2 CFG, one denoise step = "
+                     f"{len(plan)} SpatialAttnProcessor2_0 calls ({args.placement}-block attn1 placement), "
+                     f"consistent branch, sa32=sa64={args.sa}"),
+        "frames": args.frames, "cfg": 2, "height": args.res, "width": args.res, "sa": args.sa,
+        "layers": len(plan), "placement": args.placement, "gate": "forced consistent (cur_step=25)",
+        "parallelism": "single GPU" if n_gpus == 1 else f"(cfg,frame) units sharded over {n_gpus} GPUs",
+        "l2": "each layer has its own input latents; per-step working set (inputs + q/k/v/o) far exceeds the 126 MB L2",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200_arm(args):
+    import torch.distributed as dist
+
+    import spider_b200
+    from spider_b200 import native
+    from spider_b200.install import make_processor_class
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun: python -m torch.distributed.run --nproc-per-node "
+                             f"{args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...")
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: no CUDA device visible and there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    native.ensure_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}[args.dtype]
+    Fl, H, W = args.frames, args.res, args.res
+    plan = layer_plan(H, W, args.placement)
+
+    host = spider_b200.StoryGlobals()
+    host.height, host.width, host.sa32, host.sa64 = H, W, args.sa, args.sa
+    host.id_length, host.total_length = Fl, Fl + 1
+    host.total_count = len(plan)
+    host.write = True
+    cls = make_processor_class(host)
+
+    sharding = None
+    units_local = 2 * Fl
+    if world > 1:
+        from spider_b200.dist import FrameSharding
+        sharding = FrameSharding(Fl, dist.group.WORLD, dev)
+        units_local = sharding.local_batch
+
+    # identical weights / masks on every rank: same seeds (the mask sample must agree across ranks)
+    torch.manual_seed(0)
+    torch.cuda.manual_seed_all(0)
+    attns, procs, hidden = [], [], []
+    for (n, c, h) in plan:
+        a = SelfAttnModule(c, h).to(dev, dtype)
+        attns.append(a)
+        p = cls(id_length=Fl, device=str(dev), dtype=torch.float16)
+        p.dist = sharding
+        procs.append(p)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    for (n, c, h) in plan:
+        hidden.append(torch.randn((units_local, n, c), device=dev, dtype=torch.float32, generator=g).to(dtype))
+
+    # the first step's masks, sampled like the driver does (Comic_Generation.py:376) in compact form
+    host.mask1024, host.mask4096 = spider_b200.cal_attn_mask_xl(Fl + 1, Fl, args.sa, args.sa, H, W, device=str(dev),
+                                                                dtype=torch.float16)
+    real_random = random.random
+    random.random = lambda: 0.999   # gate forced open: every call takes the consistent branch (:98-103)
+
+    used_masks = []   # (mask1024, mask4096) used by each timed step, to read K_f back after timing
+
+    def step(record=False):
+        host.cur_step = 25       # the bank entry of step 25 is overwritten each time (bounded memory)
+        host.attn_count = 0
+        if record:
+            used_masks.append((host.mask1024, host.mask4096))
+        out = None
+        for a, p, x in zip(attns, procs, hidden):
+            out = p(a, x)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    try:
+        with torch.no_grad():
+            for _ in range(max(args.warmup, 3)):
+                step()
+            barrier()
+
+            # ------------------------------------------------------------------ value: device-resident inputs
+            native.reset_launch_counters()
+            native.ATTN_EVENTS = []
+            sampler = ClockSampler(local_rank) if rank == 0 else None
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                step(record=True)
+            e1.record()
+            barrier()
+            ms_total = e0.elapsed_time(e1)
+            clocks = sampler.stop() if sampler else None
+            launches = dict(native.LAUNCHES)
+            attn_events = native.ATTN_EVENTS
+            native.ATTN_EVENTS = None
+            attn_ms = sum(a.elapsed_time(b) for a, b, *_ in attn_events)
+
+            # algorithmic FLOPs of the timed steps from the index lists that were actually used
+            n32 = (H // 32) * (W // 32)
+            flops_total = 0.0
+            for (m32, m16) in used_masks:
+                c32 = m32.lists(dev)[1][:Fl].tolist()
+                c16 = m16.lists(dev)[1][:Fl].tolist()
+                for (n, c, h) in plan:
+                    flops_total += attn_flops(n, h, c32 if n == n32 else c16)
+            # every rank computed its share of the same global work; flops_total is the WHOLE job
+
+            # ------------------------------------------------------------------ e2e: host buffers in the timed region
+            e2e = None
+            if not args.no_e2e:
+                e2e = run_e2e(args, step_layers=(attns, procs, hidden), host=host, dev=dev, barrier=barrier,
+                              flops_per_step=flops_total / args.steps)
+    finally:
+        random.random = real_random
+
+    if world > 1:
+        t = torch.tensor([ms_total, attn_ms, e2e["ms"] if e2e else 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, attn_ms = float(t[0]), float(t[1])
+        if e2e:
+            e2e["ms"] = float(t[2])
+        lt = torch.tensor([sum(launches.values())], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        total_launches = int(lt[0])
+    else:
+        total_launches = sum(launches.values())
+
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = flops_total / args.steps / (ms_step * 1e-3) / 1e12
+        peaks = load_peaks()
+        n_attn = max(1, len(attn_events))
+        achieved = flops_total / world / (attn_ms * 1e-3) / 1e12 if attn_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args, world),
+            "tflop_per_step": round(flops_total / args.steps / 1e12, 4),
+            "gpu_launches": total_launches,
+            "launches_by_entry": launches,
+            "clocks": clocks,
+            "roofline": {
+                "kernel": "csa_attn_kernel (tcgen05/TMEM flash attention over compacted keys)",
+                "bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["bf16_tflops"], "unit": UNIT,
+                "frac": round(achieved / peaks["bf16_tflops"], 4),
+                "peak_source": peaks["source"], "peak_sustained": peaks.get("bf16_tflops_sustained"),
+                "frac_of_sustained": (round(achieved / peaks["bf16_tflops_sustained"], 4)
+                                      if peaks.get("bf16_tflops_sustained") else None),
+                "launches_timed": len(attn_events), "avg_launch_ms": round(attn_ms / n_attn, 5),
+                "attn_share_of_step": round(attn_ms / ms_total, 4),
+                "traffic": load_traffic(),
+            },
+        }
+        if e2e:
+            line["e2e"] = {"value": round(flops_total / args.steps / (e2e["ms"] / args.steps * 1e-3) / 1e12, 2),
+                           "unit": UNIT, "ms_per_step": round(e2e["ms"] / args.steps, 4),
+                           "h2d_bytes_per_step": e2e["h2d"] * world, "d2h_bytes_per_step": e2e["d2h"] * world}
+        if world == 1 and not args.no_cpu:
+            base = cpu_reference_sample(args, 2)
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, step_layers, host, dev, barrier, flops_per_step):
+    """The same step through the same processor calls with HOST buffers: per layer the latents are copied from pinned
+    host memory to the device (copy stream, one layer ahead of the compute), the processor runs, and the layer's
+    output is copied back to pinned host memory (second copy stream)."""
+    attns, procs, hidden = step_layers
+    host_in = [x.cpu().pin_memory() for x in hidden]
+    host_out = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in host_in]
+    h2d = sum(x.numel() * x.element_size() for x in host_in)
+    d2h = sum(x.numel() * x.element_size() for x in host_out)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    main = torch.cuda.current_stream(dev)
+    depth = 3
+    shapes = sorted({tuple(x.shape) for x in hidden})
+    ring = {s: [torch.empty(s, device=dev, dtype=hidden[0].dtype) for _ in range(depth)] for s in shapes}
+    ring_free = {s: [None] * depth for s in shapes}   # event: compute finished reading this slot
+    n = len(hidden)
+
+    def e2e_step():
+        host.cur_step = 25
+        host.attn_count = 0
+        ready = [None] * n
+        slots = [None] * n
+        counters = {s: 0 for s in shapes}
+
+        def issue_h2d(i):
+            s = tuple(hidden[i].shape)
+            k = counters[s] % depth
+            counters[s] += 1
+            with torch.cuda.stream(s_in):
+                if ring_free[s][k] is not None:
+                    s_in.wait_event(ring_free[s][k])
+                ring[s][k].copy_(host_in[i], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            ready[i] = ev
+            slots[i] = (s, k)
+
+        issue_h2d(0)
+        if n > 1:
+            issue_h2d(1)
+        outs = []
+        for i in range(n):
+            if i + 2 < n:
+                issue_h2d(i + 2)
+            main.wait_event(ready[i])
+            s, k = slots[i]
+            out = procs[i](attns[i], ring[s][k])
+            done = torch.cuda.Event()
+            done.record(main)
+            ring_free[s][k] = done
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                host_out[i].copy_(out, non_blocking=True)
+            out.record_stream(s_out)
+            outs.append(out)
+        main.wait_stream(s_out)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    return {"ms": e0.elapsed_time(e1), "h2d": h2d, "d2h": d2h}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        p["source"] = "MEASURED_PEAKS.json (measured on this pool: cuBLAS bf16 8192^3 burst)"
+        return p
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
+
+
+def load_traffic():
+    """dram bytes per attention launch from the committed `ncu --set full` capture, if one has been summarised."""
+    path = os.path.join(ROOT, "profiles", "attn_traffic.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return json.load(f).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            return None
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--frames", type=int, default=4, help="identity frames of the story (id_length)")
+    ap.add_argument("--res", type=int, default=1024, help="image height = width in pixels")
+    ap.add_argument("--sa", type=float, default=0.5, help="sa32 = sa64 sampling rate")
+    ap.add_argument("--placement", choices=["up", "all"], default="up",
+                    help="up: the reference's placement (36 up-block attn1 layers); all: all 70 attn1 layers")
+    ap.add_argument("--dtype", choices=["bf16", "fp16"], default="bf16")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()
