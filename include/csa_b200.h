@@ -17,6 +17,10 @@
  *                            torch.cat of bank and current frames at :92 (two K/V sources are read in place).
  *   csa_gather_rows       <- the row selection implied by the mask when K/V rows have to be materialised
  *                            contiguously (multi-GPU exchange of the sampled rows; bank export).
+ *   csa_sample_ranges,    <- the observation that the sampled vector of gradio_utils.py:257-261 is ONE list shared by
+ *   csa_gather_kv            every frame, CFG half and head: the sampled K/V rows are made contiguous once per layer
+ *                            (HBM-bound) and frame f then attends two runs of that buffer plus its own block, so the
+ *                            attention kernel streams plain TMA tiles instead of re-gathering rows in every CTA.
  *
  * Conventions: all pointers are DEVICE pointers unless stated; no function allocates, frees or synchronises;
  * `stream` is a cudaStream_t passed as void*; every function returns 0 on success, a negative CSA_E_* on a bad
@@ -32,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CSA_ABI_VERSION 1
+#define CSA_ABI_VERSION 2
 
 #define CSA_E_BADARG (-1)   /* null pointer, non-positive size, misaligned pointer/stride */
 #define CSA_E_SHAPE (-2)    /* unsupported geometry (head_dim != 64, row stride not 16-byte aligned, ...) */
@@ -87,6 +91,28 @@ int csa_gather_rows(const void* src, int64_t src_ld_bytes, int32_t row_base, con
                     int32_t row_bytes, void* stream);
 
 /*
+ * Per-frame runs of the sampled list.  `s_idx[0 .. *s_count)` is the ascending list S of sampled key positions
+ * (columns < n_frames*block_n of the sample vector).  For f < n_frames, ranges[f] = {0, lo_f, hi_f, *s_count - hi_f}
+ * with lo_f / hi_f the number of entries below f*block_n / (f+1)*block_n: the two runs of S that frame f attends
+ * besides its own block (mask row f = S u block_f, gradio_utils.py:267-278).  ranges[n_frames] = {0, *s_count, 0, 0}
+ * is the read-mode row (mask[F*N:], Comic_Generation.py:106-108).  ranges: device int32[(n_frames+1)*4], 16-byte
+ * aligned.
+ */
+int csa_sample_ranges(const int32_t* s_idx, const int32_t* s_count, int32_t block_n, int32_t n_frames,
+                      int32_t* ranges, void* stream);
+
+/*
+ * Make the sampled K and V rows contiguous: for g < n_groups and i < *s_count
+ *   k_out[g*out_group_rows + i, :] = k[g*group_rows + s_idx[i], :]      (same for v)
+ * and rows [*s_count, *s_count + CSA_TILE) of every group of k_out / v_out are zero-filled (a ragged last key tile
+ * must read finite values).  Rows are `row_bytes` wide (multiple of 16); leading dimensions in bytes;
+ * out_group_rows >= max_rows + CSA_TILE where max_rows bounds *s_count.  HBM-bound: 2 * (read + write) of the rows.
+ */
+int csa_gather_kv(const void* k, const void* v, int64_t ld_bytes, int32_t group_rows, int32_t n_groups,
+                  const int32_t* s_idx, const int32_t* s_count, int32_t max_rows, void* k_out, void* v_out,
+                  int64_t out_ld_bytes, int32_t out_group_rows, int32_t row_bytes, void* stream);
+
+/*
  * Flash attention over compacted keys, head_dim 64, fp16 or bf16 in/out, fp32 softmax and accumulation.
  *
  * Work is organised as n_groups (the CFG halves, which never mix: Comic_Generation.py:148) x n_frames query
@@ -96,12 +122,17 @@ int csa_gather_rows(const void* src, int64_t src_ld_bytes, int32_t row_base, con
  *   gathered    rows  g*a_group_rows + idx[list][0 .. counts[list] + g_adjust)  of k_a / v_a,
  *               list = list_base + f*list_step  (disabled when list_base < 0)
  *   contig A    rows  g*a_group_rows + ca_start + f*ca_step + [0, ca_len)        of k_a / v_a
+ *               or, when `ranges` is given, the two device-resident runs r = ranges[range_base + f*range_step]:
+ *               g*a_group_rows + r[0] + [0, r[1])  and  g*a_group_rows + r[2] + [0, r[3])   (see csa_sample_ranges)
  *   contig B    rows  g*b_group_rows + cb_start + f*cb_step + [0, cb_len)        of k_b / v_b
  *
  * which covers the four branches of the reference processor:
- *   write, consistent (:129-196)   gathered with list f over A = this call's K/V          (mask[:F*N,:F*N])
- *   read, consistent               gathered list F minus the own block (g_adjust = -N) over A = id_bank K/V,
- *                                  contig B = this call's K/V                                  (mask[F*N:])
+ *   write, consistent (:129-196)   A = sampled K/V rows of this call (csa_gather_kv), ranges[f]; contig B = own
+ *                                  frame.  Generic alternative: gathered with list f over A = this call's K/V
+ *                                  (in-kernel TMA gather4)                                     (mask[:F*N,:F*N])
+ *   read, consistent               A = sampled id_bank K/V rows, ranges[F]; contig B = this call's K/V.  Generic
+ *                                  alternative: gathered list F minus the own block (g_adjust = -N) over A =
+ *                                  id_bank K/V                                                 (mask[F*N:])
  *   read, early steps (:94-96)     contig A = all F*N bank rows, contig B = own frame
  *   standard (:198-268, enc=None)  contig B = own frame
  * Softmax is permutation invariant, so the segment order need not equal the reference's key order.
@@ -147,6 +178,10 @@ typedef struct csa_attn_args {
 
   int32_t max_ctas; /* 0 = one per SM */
   int32_t flags;    /* reserved, 0 */
+
+  const int32_t* ranges; /* optional device int32[...][4], replaces ca_* (see above); 16-byte aligned */
+  int32_t range_base;
+  int32_t range_step;
 } csa_attn_args_t;
 
 int csa_attn_fwd(const csa_attn_args_t* args, void* stream);

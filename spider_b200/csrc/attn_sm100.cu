@@ -28,6 +28,8 @@ constexpr int kTileBytes = kBN * kHD * 2;
 constexpr int kKStages = 4;
 constexpr int kVStages = 4;
 constexpr int kThreads = 384;
+constexpr int kRegsCtl = 88;       // producer / MMA / allocator warps after setmaxnreg.dec
+constexpr int kRegsSoftmax = 208;  // softmax warps after setmaxnreg.inc: (168-56)*128 == (224-168)*256
 
 // TMEM column map (fp32 columns)
 constexpr uint32_t kColS = 0;    // S0 at 0, S1 at 128
@@ -41,7 +43,7 @@ struct __align__(1024) AttnSmem {
   uint64_t q_full[2], q_empty[2];
   uint64_t k_full[kKStages], k_empty[kKStages];
   uint64_t v_full[kVStages], v_empty[kVStages];
-  uint64_t s_full[2], p_ready[2], o_done[2];
+  uint64_t s_full[2], s_free[2], p_ready[2], o_done[2];
   uint32_t tmem_base;
 };
 
@@ -63,9 +65,13 @@ struct AttnKernelParams {
   int32_t list_base, list_step, g_adjust;
   int32_t ca_start, ca_step, ca_len;
   int32_t cb_start, cb_step, cb_len;
+  const int32_t* ranges;  // optional: per list 4 ints {start1, len1, start2, len2}: two runs of A (device-resident)
+  int32_t range_base, range_step;
   float scale_log2;
   uint32_t* dbg;  // host-mapped watchdog record (may be null)
 };
+
+constexpr int kMaxSeg = 3;  // contiguous runs per unit: up to two runs of source A and one of source B
 
 struct Unit {
   int g, f, h, qp;
@@ -73,9 +79,9 @@ struct Unit {
   int ng;      // gathered keys
   const int32_t* gidx;
   int a_base;  // row offset of this group in A
-  int ca_row, ca_len;
-  int cb_row, cb_len;
-  int tg, ta, tb, total;
+  int seg_row[kMaxSeg], seg_len[kMaxSeg], seg_tiles[kMaxSeg];
+  int seg_b;   // index of the first segment that lives in source B (segments before it are in A)
+  int tg, total;
 };
 
 __device__ __forceinline__ Unit decode_unit(const AttnKernelParams& p, int u) {
@@ -96,27 +102,55 @@ __device__ __forceinline__ Unit decode_unit(const AttnKernelParams& p, int u) {
     w.gidx = p.idx + static_cast<int64_t>(list) * p.idx_stride;
   }
   w.a_base = w.g * p.a_group_rows;
-  w.ca_row = w.a_base + p.ca_start + w.f * p.ca_step;
-  w.ca_len = p.ca_len;
-  w.cb_row = w.g * p.b_group_rows + p.cb_start + w.f * p.cb_step;
-  w.cb_len = p.cb_len;
+  if (p.ranges != nullptr) {
+    const int4 rg = __ldg(reinterpret_cast<const int4*>(p.ranges) + (p.range_base + w.f * p.range_step));
+    w.seg_row[0] = w.a_base + rg.x;
+    w.seg_len[0] = rg.y > 0 ? rg.y : 0;
+    w.seg_row[1] = w.a_base + rg.z;
+    w.seg_len[1] = rg.w > 0 ? rg.w : 0;
+  } else {
+    w.seg_row[0] = w.a_base + p.ca_start + w.f * p.ca_step;
+    w.seg_len[0] = p.ca_len;
+    w.seg_row[1] = 0;
+    w.seg_len[1] = 0;
+  }
+  w.seg_b = 2;
+  w.seg_row[2] = w.g * p.b_group_rows + p.cb_start + w.f * p.cb_step;
+  w.seg_len[2] = p.cb_len;
   w.tg = (w.ng + kBN - 1) / kBN;
-  w.ta = (w.ca_len + kBN - 1) / kBN;
-  w.tb = (w.cb_len + kBN - 1) / kBN;
-  w.total = w.tg + w.ta + w.tb;
+  w.total = w.tg;
+#pragma unroll
+  for (int i = 0; i < kMaxSeg; ++i) {
+    w.seg_tiles[i] = (w.seg_len[i] + kBN - 1) / kBN;
+    w.total += w.seg_tiles[i];
+  }
   return w;
+}
+
+// tile t of the unit -> segment (-1 = gathered) and tile index inside it
+__device__ __forceinline__ void locate_tile(const Unit& w, int t, int& seg, int& local) {
+  seg = -1;
+  local = t;
+  if (t < w.tg) return;
+  local -= w.tg;
+#pragma unroll
+  for (int i = 0; i < kMaxSeg; ++i) {
+    if (seg < 0) {
+      if (local < w.seg_tiles[i]) {
+        seg = i;
+      } else {
+        local -= w.seg_tiles[i];
+      }
+    }
+  }
 }
 
 // number of valid keys in tile t of the unit
 __device__ __forceinline__ int tile_valid(const Unit& w, int t) {
-  int rem;
-  if (t < w.tg) {
-    rem = w.ng - t * kBN;
-  } else if (t < w.tg + w.ta) {
-    rem = w.ca_len - (t - w.tg) * kBN;
-  } else {
-    rem = w.cb_len - (t - w.tg - w.ta) * kBN;
-  }
+  int seg, local;
+  locate_tile(w, t, seg, local);
+  const int len = seg < 0 ? w.ng : (seg == 0 ? w.seg_len[0] : (seg == 1 ? w.seg_len[1] : w.seg_len[2]));
+  const int rem = len - local * kBN;
   return rem < kBN ? rem : kBN;
 }
 
@@ -142,7 +176,8 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       mbar_init(smem_u32(&sm.q_full[i]), 1);
       mbar_init(smem_u32(&sm.q_empty[i]), 1);
       mbar_init(smem_u32(&sm.s_full[i]), 1);
-      mbar_init(smem_u32(&sm.p_ready[i]), kBM);
+      mbar_init(smem_u32(&sm.s_free[i]), kBM / 32);
+      mbar_init(smem_u32(&sm.p_ready[i]), kBM / 32);
       mbar_init(smem_u32(&sm.o_done[i]), 1);
     }
     for (int i = 0; i < kKStages; ++i) {
@@ -163,7 +198,10 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
+  // the softmax warpgroups keep a whole 128-column score row per thread: hand them the registers of warps 0-3
+  // (setmaxnreg sits at the top of each role branch so that ptxas budgets every branch separately)
   if (warp == 0) {
+    setmaxnreg_dec<kRegsCtl>();
     // =========================================================================================== producer
     int ks = 0, vs = 0;
     uint32_t kph = 0, vph = 0, qph = 0;
@@ -215,14 +253,14 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
           iv.y += w.a_base;
           iv.z += w.a_base;
           iv.w += w.a_base;
-        } else if (t < w.tg + w.ta) {
-          row0 = w.ca_row + (t - w.tg) * kBN;
-          mk = &p.tm_ka;
-          mv = &p.tm_va;
         } else {
-          row0 = w.cb_row + (t - w.tg - w.ta) * kBN;
-          mk = &p.tm_kb;
-          mv = &p.tm_vb;
+          int seg, local;
+          locate_tile(w, t, seg, local);
+          const int srow = seg == 0 ? w.seg_row[0] : (seg == 1 ? w.seg_row[1] : w.seg_row[2]);
+          row0 = srow + local * kBN;
+          const bool in_b = seg >= w.seg_b;
+          mk = in_b ? &p.tm_kb : &p.tm_ka;
+          mv = in_b ? &p.tm_vb : &p.tm_va;
         }
         // ---- K
         if (lane == 0) {
@@ -252,6 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // =========================================================================================== MMA issue
+    setmaxnreg_dec<kRegsCtl>();
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc(kBM, kBN, kBF16 ? 1 : 0, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(kBM, kHD, kBF16 ? 1 : 0, 0, 1);
@@ -281,17 +320,23 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         }
       };
 
+      uint32_t fph0 = 0, fph1 = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         const Unit w = decode_unit(p, u);
         if (w.total == 0) continue;
-        // prologue: S0 = Q0 K0^T, S1 = Q1 K0^T
+        // prologue: S0 = Q0 K0^T, S1 = Q1 K0^T.  Every QK waits for the softmax warps to have pulled the previous
+        // S of that Q tile into registers (s_free; pre-arrived once at kernel start).
         mbar_wait(smem_u32(&sm.q_full[0]), qph, 0x200, p.dbg);
         mbar_wait(smem_u32(&sm.k_full[ks]), kph, 0x201, p.dbg);
+        mbar_wait(smem_u32(&sm.s_free[0]), fph0, 0x203, p.dbg);
+        fph0 ^= 1;
         tc_fence_after();
         issue_qk(0, ks);
         tc_commit(smem_u32(&sm.s_full[0]));
         if (w.total == 1) tc_commit(smem_u32(&sm.q_empty[0]));
         mbar_wait(smem_u32(&sm.q_full[1]), qph, 0x202, p.dbg);
+        mbar_wait(smem_u32(&sm.s_free[1]), fph1, 0x204, p.dbg);
+        fph1 ^= 1;
         tc_fence_after();
         issue_qk(1, ks);
         tc_commit(smem_u32(&sm.s_full[1]));
@@ -303,6 +348,17 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         for (int j = 0; j < w.total; ++j) {
           const bool more = (j + 1 < w.total);
           const bool last_qk = (j + 2 == w.total);
+          // S(j+1) of Q tile 0 as soon as its registers are free: the tensor core runs QK(j+1) while the softmax
+          // warps are still in the exp phase of tile j
+          if (more) {
+            mbar_wait(smem_u32(&sm.k_full[ks]), kph, 0x212, p.dbg);
+            mbar_wait(smem_u32(&sm.s_free[0]), fph0, 0x214, p.dbg);
+            fph0 ^= 1;
+            tc_fence_after();
+            issue_qk(0, ks);
+            tc_commit(smem_u32(&sm.s_full[0]));
+            if (last_qk) tc_commit(smem_u32(&sm.q_empty[0]));
+          }
           mbar_wait(smem_u32(&sm.v_full[vs]), vph, 0x210, p.dbg);
           mbar_wait(smem_u32(&sm.p_ready[0]), pph0, 0x211, p.dbg);
           pph0 ^= 1;
@@ -310,11 +366,14 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
           issue_pv(0, vs, j > 0);
           tc_commit(smem_u32(&sm.o_done[0]));
           if (more) {
-            mbar_wait(smem_u32(&sm.k_full[ks]), kph, 0x212, p.dbg);
+            mbar_wait(smem_u32(&sm.s_free[1]), fph1, 0x215, p.dbg);
+            fph1 ^= 1;
             tc_fence_after();
-            issue_qk(0, ks);
-            tc_commit(smem_u32(&sm.s_full[0]));
-            if (last_qk) tc_commit(smem_u32(&sm.q_empty[0]));
+            issue_qk(1, ks);
+            tc_commit(smem_u32(&sm.s_full[1]));
+            tc_commit(smem_u32(&sm.k_empty[ks]));
+            if (last_qk) tc_commit(smem_u32(&sm.q_empty[1]));
+            if (++ks == kKStages) { ks = 0; kph ^= 1; }
           }
           mbar_wait(smem_u32(&sm.p_ready[1]), pph1, 0x213, p.dbg);
           pph1 ^= 1;
@@ -323,18 +382,14 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
           tc_commit(smem_u32(&sm.o_done[1]));
           tc_commit(smem_u32(&sm.v_empty[vs]));
           if (++vs == kVStages) { vs = 0; vph ^= 1; }
-          if (more) {
-            issue_qk(1, ks);
-            tc_commit(smem_u32(&sm.s_full[1]));
-            tc_commit(smem_u32(&sm.k_empty[ks]));
-            if (last_qk) tc_commit(smem_u32(&sm.q_empty[1]));
-            if (++ks == kKStages) { ks = 0; kph ^= 1; }
-          }
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    setmaxnreg_dec<kRegsCtl>();
+  } else {
     // =========================================================================================== softmax
+    setmaxnreg_inc<kRegsSoftmax>();
     const int s = (warp - 4) >> 2;              // Q tile of this warpgroup
     const int row = ((warp & 3) << 5) | lane;   // query row inside the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) << 5) << 16;
@@ -342,11 +397,15 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
     const uint32_t tO = tmem + lane_base + kColO + s * kHD;
     const uint32_t tP = tmem + lane_base + kColP + s * (kBN / 2);
     const uint32_t bar_s = smem_u32(&sm.s_full[s]);
+    const uint32_t bar_f = smem_u32(&sm.s_free[s]);
     const uint32_t bar_p = smem_u32(&sm.p_ready[s]);
     const uint32_t bar_o = smem_u32(&sm.o_done[s]);
     const float sc = p.scale_log2;
+    const uint64_t sc2 = pack_f2(sc, sc);
     uint32_t sph = 0;
     uint32_t od = 0;  // PV completions on o_done[s] before the current unit
+
+    if (lane == 0) mbar_arrive(bar_f);  // S is free before the first QK of the kernel
 
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const Unit w = decode_unit(p, u);
@@ -374,6 +433,10 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         tmem_ld32(tS + 64, sv[2]);
         tmem_ld32(tS + 96, sv[3]);
         tc_wait_ld();
+        // the score row now lives in registers: let the tensor core overwrite S with the next tile's scores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_f);
 
         const int valid = tile_valid(w, j);
         if (valid < kBN) {
@@ -383,21 +446,23 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
             for (int i = 0; i < 32; ++i)
               if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
         }
-        float mx = -INFINITY;
+        // row max: 4 independent chains of 3-input max
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
-        const float m_new = fmaxf(m, mx * sc);
+          for (int i = 0; i < 32; i += 2)
+            mx[(i >> 1) & 3] = fmax3(mx[(i >> 1) & 3], __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+        const float m_new = fmaxf(m, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sc);
 
         if (j == 0) {
           m = m_new;
         } else {
+          // P and O of this Q tile are still being read by the PV of tile j-1 until o_done completes
+          mbar_wait(bar_o, (od + j - 1) & 1, 0x310 + s, p.dbg);
+          tc_fence_after();
           const bool need = m_new > m + 8.0f;
           if (__any_sync(0xffffffffu, need)) {
-            // O still holds the accumulation up to tile j-1: make sure that MMA has retired, then rescale.
-            mbar_wait(bar_o, (od + j - 1) & 1, 0x310 + s, p.dbg);
-            tc_fence_after();
             const float alpha = need ? fast_exp2(m - m_new) : 1.0f;
             if (need) m = m_new;
             l *= alpha;
@@ -410,27 +475,38 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
               for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
               tmem_st32(tO + c * 32, ov);
             }
-            tc_wait_st();
           }
         }
 
-        // P = exp2(S*scale - m), row sum, pack to 16 bit, store to TMEM
+        // P = exp2(S*scale - m) in chunks of 32 keys: FFMA2 -> MUFU.EX2 -> FADD2 row sum -> pack -> TMEM
+        const uint64_t nm2 = pack_f2(-m, -m);
+        uint64_t ls[2] = {0ull, 0ull};
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t pk[32];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int col = c * 64 + 2 * i;
-            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[col >> 5][col & 31]), sc, -m));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[(col + 1) >> 5][(col + 1) & 31]), sc, -m));
-            l += p0 + p1;
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t x2 =
+                ffma2(pack_f2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
+            float x0, x1;
+            unpack_f2(x2, x0, x1);
+            const float p0 = fast_exp2(x0);
+            const float p1 = fast_exp2(x1);
+            ls[i & 1] = fadd2(ls[i & 1], pack_f2(p0, p1));
             pk[i] = pack2<kBF16>(p0, p1);
           }
-          tmem_st32(tP + c * 32, pk);
+          tmem_st16(tP + c * 16, pk);
+        }
+        {
+          float a0, a1, b0, b1;
+          unpack_f2(ls[0], a0, a1);
+          unpack_f2(ls[1], b0, b1);
+          l += (a0 + a1) + (b0 + b1);
         }
         tc_wait_st();
         tc_fence_before();
-        mbar_arrive(bar_p);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p);
       }
 
       // epilogue: wait for the last PV, normalise, store
@@ -500,7 +576,8 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
     return set_error(CSA_E_BADARG, "csa_attn_fwd: non-positive geometry");
   if (!a->q || !a->o) return set_error(CSA_E_BADARG, "csa_attn_fwd: null q/o");
   const bool use_g = a->list_base >= 0;
-  const bool use_a = use_g || a->ca_len > 0;
+  const bool use_r = a->ranges != nullptr;
+  const bool use_a = use_g || use_r || a->ca_len > 0;
   const bool use_b = a->cb_len > 0;
   if (!use_a && !use_b) return set_error(CSA_E_BADARG, "csa_attn_fwd: no key segment enabled");
   if (use_a && (!a->k_a || !a->v_a)) return set_error(CSA_E_BADARG, "csa_attn_fwd: null k_a/v_a");
@@ -515,6 +592,8 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
       (use_b && (!aligned16(a->k_b) || !aligned16(a->v_b))))
     return set_error(CSA_E_BADARG, "csa_attn_fwd: pointers must be 16-byte aligned");
   if (a->ca_len < 0 || a->cb_len < 0) return set_error(CSA_E_BADARG, "csa_attn_fwd: negative segment length");
+  if (use_r && (!aligned16(a->ranges) || a->ca_len != 0))
+    return set_error(CSA_E_BADARG, "csa_attn_fwd: ranges must be 16-byte aligned and exclude ca_len");
 
   AttnKernelParams p;
   memset(&p, 0, sizeof(p));
@@ -560,6 +639,9 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
   p.cb_start = a->cb_start;
   p.cb_step = a->cb_step;
   p.cb_len = a->cb_len;
+  p.ranges = a->ranges;
+  p.range_base = a->range_base;
+  p.range_step = a->range_step;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.dbg = debug_record_devptr();
 

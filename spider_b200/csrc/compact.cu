@@ -135,6 +135,60 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restr
   }
 }
 
+
+// ranges[f] = {0, lo_f, hi_f, count - hi_f} (binary searches in the ascending list), ranges[n_frames] = {0,count,0,0}
+__global__ void sample_ranges_kernel(const int32_t* __restrict__ s_idx, const int32_t* __restrict__ s_count,
+                                     int block_n, int n_frames, int32_t* __restrict__ ranges) {
+  const int f = threadIdx.x;
+  if (f > n_frames) return;
+  const int count = __ldg(s_count);
+  auto lower_bound = [&](int key) {
+    int lo = 0, hi = count;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(s_idx + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  int4 r;
+  if (f == n_frames) {
+    r = make_int4(0, count, 0, 0);
+  } else {
+    const int lo = lower_bound(f * block_n);
+    const int hi = lower_bound((f + 1) * block_n);
+    r = make_int4(0, lo, hi, count - hi);
+  }
+  reinterpret_cast<int4*>(ranges)[f] = r;
+}
+
+// grid.y = group * 2 + (0: K, 1: V); one warp per destination row, 16 bytes per lane per step; rows in
+// [count, count + CSA_TILE) are zero-filled
+__global__ void __launch_bounds__(256) gather_kv_kernel(const uint8_t* __restrict__ k, const uint8_t* __restrict__ v,
+                                                        int64_t ld, int group_rows, const int32_t* __restrict__ idx,
+                                                        const int32_t* __restrict__ count, int max_rows,
+                                                        uint8_t* __restrict__ k_out, uint8_t* __restrict__ v_out,
+                                                        int64_t out_ld, int out_group_rows, int row_bytes) {
+  int n = __ldg(count);
+  n = n < max_rows ? n : max_rows;
+  const int g = blockIdx.y >> 1;
+  const uint8_t* src = (blockIdx.y & 1) ? v : k;
+  uint8_t* dst = ((blockIdx.y & 1) ? v_out : k_out) + static_cast<int64_t>(g) * out_group_rows * out_ld;
+  src += static_cast<int64_t>(g) * group_rows * ld;
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int vecs = row_bytes >> 4;
+  for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n + CSA_TILE;
+       i += gridDim.x * warps_per_block) {
+    uint4* d = reinterpret_cast<uint4*>(dst + static_cast<int64_t>(i) * out_ld);
+    if (i < n) {
+      const uint4* s = reinterpret_cast<const uint4*>(src + static_cast<int64_t>(__ldg(idx + i)) * ld);
+      for (int c = lane; c < vecs; c += 32) d[c] = __ldg(s + c);
+    } else {
+      for (int c = lane; c < vecs; c += 32) d[c] = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
 }  // namespace csa
 
 using namespace csa;
@@ -189,5 +243,38 @@ extern "C" int csa_gather_rows(const void* src, int64_t src_ld_bytes, int32_t ro
       static_cast<uint8_t*>(dst), dst_ld_bytes, row_bytes);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(static_cast<int>(e), "gather_rows_kernel: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int csa_sample_ranges(const int32_t* s_idx, const int32_t* s_count, int32_t block_n, int32_t n_frames,
+                                 int32_t* ranges, void* stream) {
+  if (!s_idx || !s_count || !ranges) return set_error(CSA_E_BADARG, "csa_sample_ranges: null pointer");
+  if (block_n <= 0 || n_frames <= 0 || n_frames >= 1024 || (reinterpret_cast<uintptr_t>(ranges) & 15))
+    return set_error(CSA_E_BADARG, "csa_sample_ranges: bad sizes or unaligned ranges");
+  const int threads = (n_frames + 1 + 31) / 32 * 32;
+  sample_ranges_kernel<<<1, threads, 0, static_cast<cudaStream_t>(stream)>>>(s_idx, s_count, block_n, n_frames, ranges);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(static_cast<int>(e), "sample_ranges_kernel: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int csa_gather_kv(const void* k, const void* v, int64_t ld_bytes, int32_t group_rows, int32_t n_groups,
+                             const int32_t* s_idx, const int32_t* s_count, int32_t max_rows, void* k_out, void* v_out,
+                             int64_t out_ld_bytes, int32_t out_group_rows, int32_t row_bytes, void* stream) {
+  if (!k || !v || !s_idx || !s_count || !k_out || !v_out) return set_error(CSA_E_BADARG, "csa_gather_kv: null pointer");
+  if (max_rows <= 0 || n_groups <= 0 || group_rows <= 0 || row_bytes <= 0 || (row_bytes & 15) || (ld_bytes & 15) ||
+      (out_ld_bytes & 15) || out_group_rows < max_rows + CSA_TILE || ((reinterpret_cast<uintptr_t>(k) |
+      reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(k_out) | reinterpret_cast<uintptr_t>(v_out)) & 15))
+    return set_error(CSA_E_BADARG, "csa_gather_kv: sizes/strides/pointers must be positive and 16-byte aligned, "
+                                   "out_group_rows >= max_rows + CSA_TILE");
+  const int warps_per_block = 8;
+  int grid = (max_rows + CSA_TILE + warps_per_block - 1) / warps_per_block;
+  const int cap = 148 * 8 / (2 * n_groups) > 0 ? 148 * 8 / (2 * n_groups) : 1;
+  if (grid > cap) grid = cap;
+  gather_kv_kernel<<<dim3(grid, 2 * n_groups), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(k), static_cast<const uint8_t*>(v), ld_bytes, group_rows, s_idx, s_count, max_rows,
+      static_cast<uint8_t*>(k_out), static_cast<uint8_t*>(v_out), out_ld_bytes, out_group_rows, row_bytes);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(static_cast<int>(e), "gather_kv_kernel: %s", cudaGetErrorString(e));
   return 0;
 }

@@ -37,6 +37,8 @@ class CompactMask:
         self._sample = sample
         self._dense = dense
         self._lists: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+        self._sample_list = None      # (s_idx, s_count, ranges) — see sample_list()
+        self.shared_sample = sample is not None   # rows are (S u own block) by construction; dense: checked
 
     # what the reference's mask tensor exposes and drivers may look at
     @property
@@ -68,6 +70,31 @@ class CompactMask:
                 # the T distinct rows are rows 0, N, 2N, ... of the dense mask (gradio_utils.py:285-286)
                 self._lists = native.compact_rows(m, T, T * N, N * m.stride(0))
         return self._lists
+
+    def sample_list(self, device=None):
+        """``(s_idx [stride] int32, s_count [1] int32, ranges [T, 4] int32)`` on the device: the ascending list S of
+        sampled key positions below ``F*N`` — ONE list shared by all frames (gradio_utils.py:257-261) — and, per
+        frame, the two runs of S it attends besides its own block (``csa_sample_ranges``).  Only valid when the mask
+        has that structure (``shared_sample``); a dense mask from outside is checked by ``from_dense``."""
+        if not self.shared_sample:
+            raise ValueError("mask rows do not share one sample vector; use lists()")
+        if self._sample_list is None:
+            T, F, N = self.total_length, self.id_length, self.n_tokens
+            if self._sample is not None:
+                src = self._sample
+                if device is not None and src.device != torch.device(device):
+                    src = self._sample = src.to(device)
+                if src.dtype != torch.bool or src.numel() != T * N or not src.is_contiguous():
+                    raise ValueError("sample vector must be a contiguous bool tensor of T*N elements")
+            else:
+                m = self._dense
+                if device is not None and m.device != torch.device(device):
+                    m = self._dense = m.to(device)
+                src = m[F * N]          # the read-mode row: S on columns < F*N (gradio_utils.py:267-278)
+            s_idx, s_count = native.compact_rows(src, 1, F * N, 0)
+            ranges = native.sample_ranges(s_idx, s_count, N, F)
+            self._sample_list = (s_idx.view(-1), s_count, ranges)
+        return self._sample_list
 
     def dense(self) -> torch.Tensor:
         """Materialise the reference's dense mask (debugging / interoperability only; O((T*N)^2) bytes)."""
@@ -112,4 +139,18 @@ def from_dense(mask: torch.Tensor, total_length: int, id_length: int, validate: 
             raise ValueError(
                 f"attention mask has {bad} 16-byte words that differ between rows of one frame block; consistent "
                 "self-attention kernels need the per-frame mask structure of cal_attn_mask_xl")
-    return CompactMask(total_length, id_length, n, dense=mask)
+    cm = CompactMask(total_length, id_length, n, dense=mask)
+    if validate:
+        # do all rows share one sample vector (row i = S u block_i)?  Only then may the sampled K/V rows be gathered
+        # once per layer; any other per-frame mask takes the generic in-kernel gather over per-frame lists.
+        rows = mask[::n]                                   # (T, T*n): the T distinct rows
+        fn = id_length * n
+        want = rows[id_length].clone()
+        want[fn:] = False
+        want = want.unsqueeze(0).repeat(total_length, 1)
+        for i in range(total_length):
+            want[i, i * n:(i + 1) * n] = True
+        cm.shared_sample = bool(torch.equal(rows, want))
+    else:
+        cm.shared_sample = True
+    return cm

@@ -18,7 +18,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcsa_b200.so")
 
-CSA_ABI_VERSION = 1
+CSA_ABI_VERSION = 2
 CSA_DTYPE_F16 = 0
 CSA_DTYPE_BF16 = 1
 CSA_TILE = 128
@@ -33,6 +33,8 @@ EXPORTED_SYMBOLS = (
     "csa_compact_rows",
     "csa_validate_mask",
     "csa_gather_rows",
+    "csa_sample_ranges",
+    "csa_gather_kv",
     "csa_attn_fwd",
 )
 
@@ -83,6 +85,9 @@ class CsaAttnArgs(ctypes.Structure):
         ("cb_len", c_int32),
         ("max_ctas", c_int32),
         ("flags", c_int32),
+        ("ranges", c_void_p),
+        ("range_base", c_int32),
+        ("range_step", c_int32),
     ]
 
 
@@ -90,7 +95,8 @@ _lib: Optional[ctypes.CDLL] = None
 
 # Launch accounting (how many of OUR kernels were launched, by entry point) and optional CUDA-event timing of the
 # attention launches on the launching stream; both are read by bench.py.
-LAUNCHES = {"csa_attn_fwd": 0, "csa_compact_rows": 0, "csa_validate_mask": 0, "csa_gather_rows": 0}
+LAUNCHES = {"csa_attn_fwd": 0, "csa_compact_rows": 0, "csa_validate_mask": 0, "csa_gather_rows": 0,
+            "csa_sample_ranges": 0, "csa_gather_kv": 0}
 ATTN_EVENTS: Optional[list] = None   # when a list: (start_event, end_event, n_groups, n_frames, n_q, heads) appended
 
 
@@ -130,6 +136,11 @@ def load() -> ctypes.CDLL:
     lib.csa_gather_rows.restype = c_int32
     lib.csa_gather_rows.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
                                     c_int64, c_int32, c_void_p]
+    lib.csa_sample_ranges.restype = c_int32
+    lib.csa_sample_ranges.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
+    lib.csa_gather_kv.restype = c_int32
+    lib.csa_gather_kv.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int32,
+                                  c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]
     lib.csa_attn_fwd.restype = c_int32
     lib.csa_attn_fwd.argtypes = [POINTER(CsaAttnArgs), c_void_p]
 
@@ -238,13 +249,46 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, max_rows: int, row_base: i
     return out
 
 
+def sample_ranges(s_idx: torch.Tensor, s_count: torch.Tensor, block_n: int, n_frames: int) -> torch.Tensor:
+    """ranges [(n_frames+1), 4] int32 (see csa_sample_ranges): the runs of the sampled list each frame attends."""
+    _require_cuda(s_idx, s_count)
+    ensure_device(s_idx.device)
+    ranges = torch.empty((n_frames + 1, 4), dtype=torch.int32, device=s_idx.device)
+    rc = load().csa_sample_ranges(s_idx.data_ptr(), s_count.data_ptr(), block_n, n_frames, ranges.data_ptr(),
+                                  _stream_ptr(s_idx))
+    _check(rc, "csa_sample_ranges")
+    LAUNCHES["csa_sample_ranges"] += 1
+    return ranges
+
+
+def gather_kv(k: torch.Tensor, v: torch.Tensor, group_rows: int, n_groups: int, s_idx: torch.Tensor,
+              s_count: torch.Tensor, max_rows: int):
+    """Sampled K/V rows made contiguous per group (see csa_gather_kv).  Returns (k_s, v_s, out_group_rows) with
+    k_s / v_s of shape (n_groups * out_group_rows, C); rows beyond the count are zero for one tile, then undefined."""
+    _require_cuda(k, v, s_idx, s_count)
+    ensure_device(k.device)
+    if k.dim() != 2 or k.stride(1) != 1 or v.shape != k.shape or v.stride(0) != k.stride(0):
+        raise CsaNativeError("gather_kv expects 2-D k/v of equal shape and row stride, unit column stride")
+    es = k.element_size()
+    out_group_rows = max_rows + CSA_TILE
+    k_s = torch.empty((n_groups * out_group_rows, k.shape[1]), dtype=k.dtype, device=k.device)
+    v_s = torch.empty_like(k_s)
+    rc = load().csa_gather_kv(k.data_ptr(), v.data_ptr(), k.stride(0) * es, group_rows, n_groups, s_idx.data_ptr(),
+                              s_count.data_ptr(), max_rows, k_s.data_ptr(), v_s.data_ptr(), k_s.stride(0) * es,
+                              out_group_rows, k.shape[1] * es, _stream_ptr(k))
+    _check(rc, "csa_gather_kv")
+    LAUNCHES["csa_gather_kv"] += 1
+    return k_s, v_s, out_group_rows
+
+
 def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_frames: int, n_q: int,
              k_a: Optional[torch.Tensor] = None, v_a: Optional[torch.Tensor] = None, a_group_rows: int = 0,
              k_b: Optional[torch.Tensor] = None, v_b: Optional[torch.Tensor] = None, b_group_rows: int = 0,
              idx: Optional[torch.Tensor] = None, counts: Optional[torch.Tensor] = None,
              list_base: int = -1, list_step: int = 0, g_adjust: int = 0,
              ca: tuple = (0, 0, 0), cb: tuple = (0, 0, 0), scale: Optional[float] = None,
-             max_ctas: int = 0) -> torch.Tensor:
+             max_ctas: int = 0, ranges: Optional[torch.Tensor] = None, range_base: int = 0,
+             range_step: int = 0) -> torch.Tensor:
     """Launch csa_attn_fwd on the current stream.  All matrices are 2-D ``(rows, heads*64)`` with unit column stride."""
     _require_cuda(q, o)
     ensure_device(q.device)
@@ -281,6 +325,10 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
     a.cb_start, a.cb_step, a.cb_len = cb
     a.max_ctas = max_ctas
     a.flags = 0
+    if ranges is not None:
+        if ranges.dtype != torch.int32 or not ranges.is_contiguous() or ranges.shape[-1] != 4:
+            raise CsaNativeError("ranges must be a contiguous int32 tensor of shape (lists, 4)")
+        a.ranges, a.range_base, a.range_step = ranges.data_ptr(), range_base, range_step
     if ATTN_EVENTS is not None:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)

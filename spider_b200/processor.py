@@ -63,11 +63,14 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
       _host            namespace holding the control globals (a module or any object with those attributes)
       bank_store       "kv" | "hidden" | "both"  — what the write pass keeps per step (``bank.py``)
       validate_masks   check dense masks supplied from outside for the per-frame structure (one sync per mask)
+      kv_gather        "pre" | "inline" — how the sampled cross-frame K/V rows reach shared memory
     """
 
     _host = GLOBALS
     bank_store = "kv"
     validate_masks = True
+    kv_gather = "pre"       # "pre": sampled K/V rows gathered once per layer (csa_gather_kv) and streamed as plain
+                            # TMA tiles; "inline": per-frame index lists, TMA gather4 inside the attention kernel
 
     def __init__(self, hidden_size=None, cross_attention_dim=None, id_length=4, device="cuda", dtype=torch.float16):
         super().__init__()
@@ -238,6 +241,15 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
         Fl = self.id_length
         if self.dist is not None:
             return self.dist.attn_write(q, k, v, o, N, heads, cm, Fl)
+        if self.kv_gather == "pre" and cm.shared_sample:
+            # mask row f = S u block_f: gather K[S], V[S] once (HBM-bound), then frame f attends the two runs of that
+            # buffer that lie outside its own block + its own block in place
+            s_idx, s_count, ranges = cm.sample_list(q.device)
+            k_s, v_s, cap = native.gather_kv(k, v, Fl * N, 2, s_idx, s_count, Fl * N)
+            native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=Fl, n_q=N,
+                            k_a=k_s, v_a=v_s, a_group_rows=cap, ranges=ranges, range_base=0, range_step=1,
+                            k_b=k, v_b=v, b_group_rows=Fl * N, cb=(0, N, N))
+            return
         idx, counts = cm.lists(q.device)
         native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=Fl, n_q=N,
                         k_a=k, v_a=v, a_group_rows=Fl * N,
@@ -256,6 +268,12 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
         if cm is None:
             native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=1, n_q=N,
                             k_a=kb, v_a=vb, a_group_rows=Fl * N, ca=(0, 0, Fl * N),
+                            k_b=k, v_b=v, b_group_rows=N, cb=(0, 0, N))
+        elif self.kv_gather == "pre" and cm.shared_sample:
+            s_idx, s_count, ranges = cm.sample_list(q.device)
+            k_s, v_s, cap = native.gather_kv(kb, vb, Fl * N, 2, s_idx, s_count, Fl * N)
+            native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=1, n_q=N,
+                            k_a=k_s, v_a=v_s, a_group_rows=cap, ranges=ranges, range_base=Fl, range_step=0,
                             k_b=k, v_b=v, b_group_rows=N, cb=(0, 0, N))
         else:
             idx, counts = cm.lists(q.device)

@@ -133,6 +133,43 @@ def test_gather_rows_bit_exact():
     assert torch.equal(out2[:1000], src[idx[:1000].long()]) and float(out2[1000:].abs().sum()) == 0.0
 
 
+def test_sample_ranges_and_gather_kv_bit_exact():
+    """csa_sample_ranges / csa_gather_kv against numpy: the runs of the shared sample list S each frame attends, and
+    the sampled K/V rows made contiguous (zero-filled for one tile past the count)."""
+    for (Fl, N, C, sa, seed) in [(4, 1024, 1280, 0.5, 0), (3, 100, 64, 0.3, 1), (4, 64, 128, 0.0, 2),
+                                 (4, 64, 128, 1.0, 3), (16, 256, 640, 0.5, 4)]:
+        g = torch.Generator().manual_seed(seed)
+        T = Fl + 1
+        sample = torch.rand((T * N,), generator=g) < sa
+        cm = csa_masks.CompactMask(T, Fl, N, sample=sample.to(DEV))
+        s_idx, s_count, ranges = cm.sample_list(DEV)
+        S = np.nonzero(sample[:Fl * N].numpy())[0].astype(np.int32)
+        cnt = int(s_count.item())
+        assert cnt == S.size and np.array_equal(s_idx[:cnt].cpu().numpy(), S)
+        want = []
+        for f in range(Fl):
+            lo = int(np.searchsorted(S, f * N))
+            hi = int(np.searchsorted(S, (f + 1) * N))
+            want.append([0, lo, hi, S.size - hi])
+            # the two runs + the own block are exactly the oracle's key list of frame f
+            keys = np.concatenate([S[:lo], np.arange(f * N, (f + 1) * N), S[hi:]])
+            assert np.array_equal(np.sort(keys), rp.index_lists(rp.frame_rows(sample, T, Fl))[f].numpy()[
+                rp.index_lists(rp.frame_rows(sample, T, Fl))[f].numpy() < Fl * N])
+        want.append([0, S.size, 0, 0])
+        assert np.array_equal(ranges.cpu().numpy(), np.array(want, dtype=np.int32))
+        k = torch.randn((2 * Fl * N, C), generator=g).to(torch.bfloat16).to(DEV)
+        v = torch.randn((2 * Fl * N, C), generator=g).to(torch.bfloat16).to(DEV)
+        k_s, v_s, cap = native.gather_kv(k, v, Fl * N, 2, s_idx, s_count, Fl * N)
+        assert cap == Fl * N + native.CSA_TILE
+        Sl = torch.from_numpy(S).long().to(DEV)
+        for gi in range(2):
+            assert torch.equal(k_s[gi * cap:gi * cap + cnt], k[gi * Fl * N + Sl])
+            assert torch.equal(v_s[gi * cap:gi * cap + cnt], v[gi * Fl * N + Sl])
+            pad = min(cap, cnt + native.CSA_TILE)
+            assert float(k_s[gi * cap + cnt:gi * cap + pad].float().abs().sum()) == 0.0
+            assert float(v_s[gi * cap + cnt:gi * cap + pad].float().abs().sum()) == 0.0
+
+
 # ------------------------------------------------------------------------------------------------ attention kernel
 def _kernel_vs_oracle(Fl, N, C, heads, sa, dtype, mode, seed=0):
     """native.attn_fwd against oracle.gathered_attention (CPU fp32) on the same 16-bit inputs."""
@@ -147,12 +184,22 @@ def _kernel_vs_oracle(Fl, N, C, heads, sa, dtype, mode, seed=0):
     def mk(rows_):
         return torch.randn((rows_, C), generator=g).to(dtype)
 
+    pre = mode.endswith("_pre")     # sampled rows gathered once (csa_gather_kv) instead of in-kernel gather4
+    mode = mode[:-4] if pre else mode
+    if pre:
+        s_idx, s_count, ranges = csa_masks.CompactMask(T, Fl, N, sample=r).sample_list(DEV)
     if mode == "write":
         q, k, v = mk(2 * Fl * N), mk(2 * Fl * N), mk(2 * Fl * N)
         qd, kd, vd = q.to(DEV), k.to(DEV), v.to(DEV)
         o = torch.empty_like(qd)
-        native.attn_fwd(qd, o, heads=heads, n_groups=2, n_frames=Fl, n_q=N, k_a=kd, v_a=vd, a_group_rows=Fl * N,
-                        idx=idx, counts=counts, list_base=0, list_step=1)
+        if pre:
+            k_s, v_s, cap = native.gather_kv(kd, vd, Fl * N, 2, s_idx, s_count, Fl * N)
+            native.attn_fwd(qd, o, heads=heads, n_groups=2, n_frames=Fl, n_q=N, k_a=k_s, v_a=v_s, a_group_rows=cap,
+                            ranges=ranges, range_base=0, range_step=1, k_b=kd, v_b=vd, b_group_rows=Fl * N,
+                            cb=(0, N, N))
+        else:
+            native.attn_fwd(qd, o, heads=heads, n_groups=2, n_frames=Fl, n_q=N, k_a=kd, v_a=vd,
+                            a_group_rows=Fl * N, idx=idx, counts=counts, list_base=0, list_step=1)
         want = rp.gathered_attention(q.view(2, Fl * N, C), k.view(2, Fl * N, C), v.view(2, Fl * N, C), lists[:Fl],
                                      heads).reshape(2 * Fl * N, C)
     elif mode in ("read", "read_early"):
@@ -162,7 +209,12 @@ def _kernel_vs_oracle(Fl, N, C, heads, sa, dtype, mode, seed=0):
         o = torch.empty_like(qd)
         kw = dict(heads=heads, n_groups=2, n_frames=1, n_q=N, k_a=kb.to(DEV), v_a=vb.to(DEV), a_group_rows=Fl * N,
                   k_b=kc.to(DEV), v_b=vc.to(DEV), b_group_rows=N, cb=(0, 0, N))
-        if mode == "read":
+        if mode == "read" and pre:
+            k_s, v_s, cap = native.gather_kv(kw["k_a"], kw["v_a"], Fl * N, 2, s_idx, s_count, Fl * N)
+            kw.update(k_a=k_s, v_a=v_s, a_group_rows=cap)
+            native.attn_fwd(qd, o, ranges=ranges, range_base=Fl, range_step=0, **kw)
+            keys = lists[Fl]
+        elif mode == "read":
             native.attn_fwd(qd, o, idx=idx, counts=counts, list_base=Fl, list_step=0, g_adjust=-N, **kw)
             keys = lists[Fl]
         else:
@@ -188,7 +240,7 @@ def _kernel_vs_oracle(Fl, N, C, heads, sa, dtype, mode, seed=0):
     return _assert_close(o, want, f"{mode} F={Fl} N={N} C={C} sa={sa} {dtype}")
 
 
-@pytest.mark.parametrize("mode", ["write", "read", "read_early", "standard"])
+@pytest.mark.parametrize("mode", ["write", "write_pre", "read", "read_pre", "read_early", "standard"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_attention_modes_vs_oracle(mode, dtype):
     _kernel_vs_oracle(4, 256, 128, 2, 0.5, dtype, mode)
@@ -204,14 +256,17 @@ def test_attention_modes_vs_oracle(mode, dtype):
     (8, 128, 128, 2, 0.05),    # sparse sample: gathered tiles only
     (4, 1024, 1280, 20, 0.5),  # the 32x32 SDXL layer of BASELINE config 2
 ])
-def test_attention_write_shapes_vs_oracle(Fl, N, C, heads, sa):
-    _kernel_vs_oracle(Fl, N, C, heads, sa, torch.bfloat16, "write", seed=N + Fl)
+@pytest.mark.parametrize("gather", ["inline", "pre"])
+def test_attention_write_shapes_vs_oracle(Fl, N, C, heads, sa, gather):
+    _kernel_vs_oracle(Fl, N, C, heads, sa, torch.bfloat16, "write" if gather == "inline" else "write_pre",
+                      seed=N + Fl)
 
 
 @pytest.mark.parametrize("Fl,N,C,heads,sa", [(4, 576, 128, 2, 0.5), (3, 100, 64, 1, 0.3), (4, 1024, 1280, 20, 0.5),
                                              (4, 256, 128, 2, 0.0), (4, 256, 128, 2, 1.0)])
-def test_attention_read_shapes_vs_oracle(Fl, N, C, heads, sa):
-    _kernel_vs_oracle(Fl, N, C, heads, sa, torch.float16, "read", seed=N)
+@pytest.mark.parametrize("gather", ["inline", "pre"])
+def test_attention_read_shapes_vs_oracle(Fl, N, C, heads, sa, gather):
+    _kernel_vs_oracle(Fl, N, C, heads, sa, torch.float16, "read" if gather == "inline" else "read_pre", seed=N)
 
 
 def test_attention_strided_inputs():
@@ -285,8 +340,8 @@ def test_processor_calls_vs_reference_golden(dtype):
         _assert_close(out, torch.from_numpy(z["read_early"]), "read_early")
 
 
-@pytest.mark.parametrize("bank_store", ["kv", "hidden", "both"])
-def test_story_state_machine_vs_reference_golden(bank_store):
+@pytest.mark.parametrize("bank_store,kv_gather", [("kv", "pre"), ("hidden", "pre"), ("both", "pre"), ("kv", "inline")])
+def test_story_state_machine_vs_reference_golden(bank_store, kv_gather):
     """The whole Appendix-C scenario on the GPU: 8 write steps + 8 read steps x 3 layers, same seeds, same inputs,
     same gates, same sample vectors (processors draw them on the CPU generator like the golden run) — every call's
     output against the reference's."""
@@ -295,6 +350,7 @@ def test_story_state_machine_vs_reference_golden(bank_store):
     host = spider_b200.StoryGlobals()
     host.height, host.width, host.total_count, host.sa32, host.sa64 = H, W, 3, 0.5, 0.5
     cls = make_processor_class(host, bank_store=bank_store)
+    cls.kv_gather = kv_gather
     rp.setup_seed(2047)
     attns = [FakeAttention(C, heads) for _ in range(3)]            # consumes the torch stream like the golden run
     for li, a in enumerate(attns):
@@ -323,7 +379,7 @@ def test_story_state_machine_vs_reference_golden(bank_store):
     assert host.cur_step == int(z["final_cur_step"])
     for p, keys in zip(procs, z["bank_keys"]):
         assert sorted(p.id_bank.keys()) == list(keys)
-    print(f"story parity ({bank_store}): worst max-abs {worst[0]:.3e}, worst cos {worst[1]:.6f}")
+    print(f"story parity ({bank_store}, {kv_gather}): worst max-abs {worst[0]:.3e}, worst cos {worst[1]:.6f}")
 
 
 def test_processor_vs_oracle_config2_sizes():

@@ -39,6 +39,18 @@ def recorder(monkeypatch):
         calls.append(("validate", tuple(mask.shape), block_n))
         return torch.zeros((1,), dtype=torch.int32)
 
+    def fake_sample_ranges(s_idx, s_count, block_n, n_frames):
+        calls.append(("ranges", block_n, n_frames))
+        return torch.zeros((n_frames + 1, 4), dtype=torch.int32)
+
+    def fake_gather_kv(k, v, group_rows, n_groups, s_idx, s_count, max_rows):
+        calls.append(("gather_kv", tuple(k.shape), group_rows, n_groups, max_rows))
+        cap = max_rows + native.CSA_TILE
+        return (torch.zeros((n_groups * cap, k.shape[1]), dtype=k.dtype),
+                torch.zeros((n_groups * cap, k.shape[1]), dtype=k.dtype), cap)
+
+    monkeypatch.setattr(native, "sample_ranges", fake_sample_ranges)
+    monkeypatch.setattr(native, "gather_kv", fake_gather_kv)
     monkeypatch.setattr(native, "attn_fwd", fake_attn_fwd)
     monkeypatch.setattr(native, "compact_rows", fake_compact_rows)
     monkeypatch.setattr(native, "validate_mask", fake_validate)
@@ -116,6 +128,22 @@ def test_launch_geometry_per_branch(recorder):
         p(attn, torch.randn(2 * Fl, N, C))
         assert p._last_branch == "consistent"
         kind, kw, shapes, qshape = recorder[-1]
+        # default: sampled rows gathered once per layer, frame f attends two runs of that buffer + its own block
+        cap = Fl * N + native.CSA_TILE
+        assert (kw["n_groups"], kw["n_frames"], kw["n_q"]) == (2, Fl, N) and "list_base" not in kw
+        assert (kw["range_base"], kw["range_step"], kw["cb"]) == (0, 1, (0, N, N))
+        assert kw["a_group_rows"] == cap and shapes["k_a"] == (2 * cap, C) and shapes["k_b"] == (2 * Fl * N, C)
+        assert shapes["ranges"] == (Fl + 1, 4)
+        assert ("compact", 1, Fl * N, 0, 0, 0) in recorder and ("ranges", N, Fl) in recorder
+        assert ("gather_kv", (2 * Fl * N, C), Fl * N, 2, Fl * N) in recorder
+        # generic alternative: per-frame index lists, TMA gather4 inside the attention kernel
+        host.cur_step = 5
+        random.seed(4)   # 0.236 -> standard
+        cls.kv_gather = "inline"
+        random.seed(0)   # 0.844 -> consistent
+        p(attn, torch.randn(2 * Fl, N, C))
+        cls.kv_gather = "pre"
+        kind, kw, shapes, qshape = recorder[-1]
         assert (kw["n_groups"], kw["n_frames"], kw["n_q"], kw["list_base"], kw["list_step"]) == (2, Fl, N, 0, 1)
         assert kw["a_group_rows"] == Fl * N and shapes["k_a"] == (2 * Fl * N, C)
         assert ("compact", Fl + 1, (Fl + 1) * N, 0, N, Fl * N) in recorder
@@ -133,6 +161,14 @@ def test_launch_geometry_per_branch(recorder):
         p(attn, torch.randn(2, N, C))
         kind, kw, shapes, qshape = recorder[-1]
         assert p._last_branch == "consistent"
+        assert (kw["range_base"], kw["range_step"], kw["cb"]) == (Fl, 0, (0, 0, N)) and "list_base" not in kw
+        assert shapes["k_b"] == (2 * N, C) and kw["a_group_rows"] == Fl * N + native.CSA_TILE
+        host.cur_step = 6
+        cls.kv_gather = "inline"
+        random.seed(0)
+        p(attn, torch.randn(2, N, C))
+        cls.kv_gather = "pre"
+        kind, kw, shapes, qshape = recorder[-1]
         assert (kw["list_base"], kw["list_step"], kw["g_adjust"]) == (Fl, 0, -N) and kw["cb"] == (0, 0, N)
     with pytest.raises(KeyError):
         host.cur_step = 99
@@ -175,7 +211,22 @@ def test_dense_mask_is_validated_and_cached(recorder):
     assert sum(1 for c in recorder if c[0] == "validate") == 1
     assert sum(1 for c in recorder if c[0] == "compact") == 1
     comp = [c for c in recorder if c[0] == "compact"][0]
+    assert comp[1:] == (1, Fl * N, 0, 0, 0)          # the shared sample list S = read row restricted to F*N columns
+    cm = host._csa_dense_cache[True][1]
+    assert cm.shared_sample
+    # a per-frame mask that is NOT (S u own block) keeps the generic per-frame lists (in-kernel gather4)
+    odd = rp.cal_attn_mask_xl(Fl + 1, Fl, 0.5, 0.5, 128, 128)[0].clone()
+    odd[:N, 2 * N:3 * N] = ~odd[:N, 2 * N:3 * N]
+    host.mask1024 = odd
+    host.attn_count, host.cur_step = 0, 6
+    del recorder[:]
+    random.seed(0)
+    with torch.no_grad():
+        procs[0](attn, torch.randn(8, N, C))
+    assert not host._csa_dense_cache[True][1].shared_sample
+    comp = [c for c in recorder if c[0] == "compact"][0]
     assert comp[1:] == (Fl + 1, (Fl + 1) * N, N * (Fl + 1) * N, 0, 0)   # rows 0, N, 2N.. of the dense mask
+    assert not any(c[0] == "gather_kv" for c in recorder)
 
 
 def test_bank_entry_semantics():
