@@ -9,7 +9,7 @@
 //   warp 0      producer   TMA: Q tiles (box 64x128), K/V tiles either as one tiled load (contiguous run of keys) or
 //                          as 32 lane-parallel `tile::gather4` loads (4 indexed rows each) into the same 128B-swizzled
 //                          16 KB stage
-//   warp 1      MMA issue  one lane issues tcgen05.mma:  S = Q K^T  (SS, M128 N128 K64),  O += P V (TS: P read from
+//   warps 1, 3  MMA issue  one lane per Q tile issues tcgen05.mma:  S = Q K^T  (SS, M128 N128 K64),  O += P V (TS: P read from
 //                          TMEM as the A operand, V read MN-major from the very tile TMA wrote, M128 N64 K128)
 //   warp 2      TMEM allocator (512 columns: S0 S1 | O0 O1 | P0 P1)
 //   warps 4-7   softmax for Q tile 0 (thread == query row, no shuffles), warps 8-11 for Q tile 1.
@@ -18,6 +18,16 @@
 // Two 128-row Q tiles are ping-ponged so that the tensor core works on one tile while the other is in softmax.
 #include "ptx.cuh"
 #include "csa_internal.h"
+
+// Softmax organisation: 1 = software-pipelined (S(j+1) pulled in place while tile j is exponentiated),
+// 0 = one tile at a time.
+#ifndef CSA_SOFTMAX_PIPE
+#define CSA_SOFTMAX_PIPE 0
+#endif
+// How many of every 16 element pairs take the polynomial exp2 (FMA/ALU pipes) instead of MUFU.EX2.
+#ifndef CSA_POLY_PAIRS
+#define CSA_POLY_PAIRS 0
+#endif
 
 namespace csa {
 
@@ -35,6 +45,11 @@ constexpr int kRegsSoftmax = 208;  // softmax warps after setmaxnreg.inc: (168-5
 constexpr uint32_t kColS = 0;    // S0 at 0, S1 at 128
 constexpr uint32_t kColO = 256;  // O0 at 256, O1 at 320
 constexpr uint32_t kColP = 384;  // P0 at 384, P1 at 448 (128 16-bit values = 64 columns)
+
+// pair i of a 16-pair chunk goes to the polynomial iff it is one of CSA_POLY_PAIRS evenly spread slots
+__host__ __device__ constexpr bool poly_pair(int i) {
+  return ((i + 1) * CSA_POLY_PAIRS) / 16 != (i * CSA_POLY_PAIRS) / 16;
+}
 
 struct __align__(1024) AttnSmem {
   uint8_t q[2][kTileBytes];
@@ -182,11 +197,11 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
     }
     for (int i = 0; i < kKStages; ++i) {
       mbar_init(smem_u32(&sm.k_full[i]), 1);
-      mbar_init(smem_u32(&sm.k_empty[i]), 1);
+      mbar_init(smem_u32(&sm.k_empty[i]), 2);  // one commit per MMA stream
     }
     for (int i = 0; i < kVStages; ++i) {
       mbar_init(smem_u32(&sm.v_full[i]), 1);
-      mbar_init(smem_u32(&sm.v_empty[i]), 1);
+      mbar_init(smem_u32(&sm.v_empty[i]), 2);
     }
     fence_mbar_init();
   }
@@ -288,104 +303,77 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         if (++vs == kVStages) { vs = 0; vph ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 3) {
     // =========================================================================================== MMA issue
+    // One issuing thread per Q tile (warp 1: tile 0, warp 3: tile 1).  The two instruction streams are independent,
+    // so a Q tile whose softmax is late never blocks the MMAs of the other tile (in-order issue from ONE thread
+    // would serialise the two softmax warpgroups).  Per stream: QK(0), QK(1), then {QK(j+2), PV(j)} — the scores
+    // run two tiles ahead of the PV so that S(j+1) is in TMEM while the softmax warps exponentiate tile j.
     setmaxnreg_dec<kRegsCtl>();
     if (lane == 0) {
+      const int s = warp >> 1;  // 0 or 1
       constexpr uint32_t idesc_qk = make_idesc(kBM, kBN, kBF16 ? 1 : 0, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(kBM, kHD, kBF16 ? 1 : 0, 0, 1);
       int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0, qph = 0, pph0 = 0, pph1 = 0;
-      const uint32_t tS0 = tmem + kColS, tS1 = tmem + kColS + kBN;
-      const uint32_t tO0 = tmem + kColO, tO1 = tmem + kColO + kHD;
-      const uint32_t tP0 = tmem + kColP, tP1 = tmem + kColP + kBN / 2;
+      uint32_t kph = 0, vph = 0, qph = 0, pph = 0, fph = 0;
+      const uint32_t tS = tmem + kColS + s * kBN;
+      const uint32_t tO = tmem + kColO + s * kHD;
+      const uint32_t tP = tmem + kColP + s * (kBN / 2);
+      const uint32_t bar_qf = smem_u32(&sm.q_full[s]), bar_qe = smem_u32(&sm.q_empty[s]);
+      const uint32_t bar_sf = smem_u32(&sm.s_full[s]), bar_fr = smem_u32(&sm.s_free[s]);
+      const uint32_t bar_pr = smem_u32(&sm.p_ready[s]), bar_od = smem_u32(&sm.o_done[s]);
+      const uint64_t dq = make_sw128_desc(smem_u32(sm.q[s]));
 
-      auto issue_qk = [&](int s, int kstage) {
-        const uint64_t dq = make_sw128_desc(smem_u32(sm.q[s]));
-        const uint64_t dk = make_sw128_desc(smem_u32(sm.k[kstage]));
+      // S = Q K^T for the K tile in stage `ks`; releases the stage and, for the unit's last tile, the Q tile
+      auto qk_step = [&](bool last) {
+        mbar_wait(smem_u32(&sm.k_full[ks]), kph, 0x201 + s, p.dbg);
+        mbar_wait(bar_fr, fph, 0x203 + s, p.dbg);  // softmax has pulled the previous S into registers
+        fph ^= 1;
+        tc_fence_after();
+        const uint64_t dk = make_sw128_desc(smem_u32(sm.k[ks]));
 #pragma unroll
         for (int kk = 0; kk < kHD / 16; ++kk) {
           // advance 16 elements (32 B) along the contraction dim inside the swizzled 128 B row
-          mma_ss(s == 0 ? tS0 : tS1, dq + kk * 2, dk + kk * 2, idesc_qk, kk > 0 ? 1u : 0u);
+          mma_ss(tS, dq + kk * 2, dk + kk * 2, idesc_qk, kk > 0 ? 1u : 0u);
         }
-      };
-      auto issue_pv = [&](int s, int vstage, bool acc) {
-        const uint64_t dv = make_sw128_desc(smem_u32(sm.v[vstage]));
-#pragma unroll
-        for (int kk = 0; kk < kBN / 16; ++kk) {
-          // 16 keys = 16 rows of 128 B = 2048 B along the contraction dim (MN-major B operand);
-          // 16 16-bit P values = 8 TMEM columns
-          mma_ts(s == 0 ? tO0 : tO1, (s == 0 ? tP0 : tP1) + kk * 8, dv + kk * (2048 >> 4), idesc_pv,
-                 (acc || kk > 0) ? 1u : 0u);
-        }
+        tc_commit(bar_sf);
+        tc_commit(smem_u32(&sm.k_empty[ks]));
+        if (last) tc_commit(bar_qe);
+        if (++ks == kKStages) { ks = 0; kph ^= 1; }
       };
 
-      uint32_t fph0 = 0, fph1 = 0;
       for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
         const Unit w = decode_unit(p, u);
         if (w.total == 0) continue;
-        // prologue: S0 = Q0 K0^T, S1 = Q1 K0^T.  Every QK waits for the softmax warps to have pulled the previous
-        // S of that Q tile into registers (s_free; pre-arrived once at kernel start).
-        mbar_wait(smem_u32(&sm.q_full[0]), qph, 0x200, p.dbg);
-        mbar_wait(smem_u32(&sm.k_full[ks]), kph, 0x201, p.dbg);
-        mbar_wait(smem_u32(&sm.s_free[0]), fph0, 0x203, p.dbg);
-        fph0 ^= 1;
-        tc_fence_after();
-        issue_qk(0, ks);
-        tc_commit(smem_u32(&sm.s_full[0]));
-        if (w.total == 1) tc_commit(smem_u32(&sm.q_empty[0]));
-        mbar_wait(smem_u32(&sm.q_full[1]), qph, 0x202, p.dbg);
-        mbar_wait(smem_u32(&sm.s_free[1]), fph1, 0x204, p.dbg);
-        fph1 ^= 1;
-        tc_fence_after();
-        issue_qk(1, ks);
-        tc_commit(smem_u32(&sm.s_full[1]));
-        tc_commit(smem_u32(&sm.k_empty[ks]));
-        if (w.total == 1) tc_commit(smem_u32(&sm.q_empty[1]));
-        if (++ks == kKStages) { ks = 0; kph ^= 1; }
+        mbar_wait(bar_qf, qph, 0x200 + s, p.dbg);
         qph ^= 1;
-
+        qk_step(w.total == 1);
+        if (w.total > 1) qk_step(w.total == 2);
         for (int j = 0; j < w.total; ++j) {
-          const bool more = (j + 1 < w.total);
-          const bool last_qk = (j + 2 == w.total);
-          // S(j+1) of Q tile 0 as soon as its registers are free: the tensor core runs QK(j+1) while the softmax
-          // warps are still in the exp phase of tile j
-          if (more) {
-            mbar_wait(smem_u32(&sm.k_full[ks]), kph, 0x212, p.dbg);
-            mbar_wait(smem_u32(&sm.s_free[0]), fph0, 0x214, p.dbg);
-            fph0 ^= 1;
-            tc_fence_after();
-            issue_qk(0, ks);
-            tc_commit(smem_u32(&sm.s_full[0]));
-            if (last_qk) tc_commit(smem_u32(&sm.q_empty[0]));
-          }
-          mbar_wait(smem_u32(&sm.v_full[vs]), vph, 0x210, p.dbg);
-          mbar_wait(smem_u32(&sm.p_ready[0]), pph0, 0x211, p.dbg);
-          pph0 ^= 1;
+#if CSA_SOFTMAX_PIPE
+          if (j + 2 < w.total) qk_step(j + 3 == w.total);  // F(j+1) and P(j) arrive together: scores first
+#endif
+          mbar_wait(smem_u32(&sm.v_full[vs]), vph, 0x210 + s, p.dbg);
+          mbar_wait(bar_pr, pph, 0x212 + s, p.dbg);
+          pph ^= 1;
           tc_fence_after();
-          issue_pv(0, vs, j > 0);
-          tc_commit(smem_u32(&sm.o_done[0]));
-          if (more) {
-            mbar_wait(smem_u32(&sm.s_free[1]), fph1, 0x215, p.dbg);
-            fph1 ^= 1;
-            tc_fence_after();
-            issue_qk(1, ks);
-            tc_commit(smem_u32(&sm.s_full[1]));
-            tc_commit(smem_u32(&sm.k_empty[ks]));
-            if (last_qk) tc_commit(smem_u32(&sm.q_empty[1]));
-            if (++ks == kKStages) { ks = 0; kph ^= 1; }
+          const uint64_t dv = make_sw128_desc(smem_u32(sm.v[vs]));
+#pragma unroll
+          for (int kk = 0; kk < kBN / 16; ++kk) {
+            // 16 keys = 16 rows of 128 B = 2048 B along the contraction dim (MN-major B operand);
+            // 16 16-bit P values = 8 TMEM columns
+            mma_ts(tO, tP + kk * 8, dv + kk * (2048 >> 4), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
           }
-          mbar_wait(smem_u32(&sm.p_ready[1]), pph1, 0x213, p.dbg);
-          pph1 ^= 1;
-          tc_fence_after();
-          issue_pv(1, vs, j > 0);
-          tc_commit(smem_u32(&sm.o_done[1]));
+          tc_commit(bar_od);
           tc_commit(smem_u32(&sm.v_empty[vs]));
           if (++vs == kVStages) { vs = 0; vph ^= 1; }
+#if !CSA_SOFTMAX_PIPE
+          if (j + 2 < w.total) qk_step(j + 3 == w.total);  // F(j+1) arrives after P(j): PV first
+#endif
         }
       }
     }
-  } else if (warp < 4) {
+  } else if (warp == 2) {
     setmaxnreg_dec<kRegsCtl>();
   } else {
     // =========================================================================================== softmax
@@ -420,6 +408,137 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         }
         continue;
       }
+#if CSA_SOFTMAX_PIPE
+      float m = -INFINITY;  // running max, already multiplied by scale*log2(e)
+      float l = 0.f;
+      uint32_t sv[4][32];  // the score row of the tile being exponentiated; refilled in place with the next tile's
+      float mx[4];         // partial row maxima (unscaled) of the tile held in sv
+
+      // masks the keys beyond `valid` of chunk c and folds the chunk into the partial maxima
+      auto chunk_max = [&](const int c, const int valid) {
+        if (valid < kBN) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          mx[(i >> 1) & 3] = fmax3(mx[(i >> 1) & 3], __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+      };
+
+      // prologue: scores of the unit's first tile
+      mbar_wait(bar_s, sph, 0x300 + s, p.dbg);
+      sph ^= 1;
+      tc_fence_after();
+      tmem_ld32(tS + 0, sv[0]);
+      tmem_ld32(tS + 32, sv[1]);
+      tmem_ld32(tS + 64, sv[2]);
+      tmem_ld32(tS + 96, sv[3]);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_f);  // S may be overwritten with the next tile's scores
+      {
+        const int valid0 = tile_valid(w, 0);
+        mx[0] = mx[1] = mx[2] = mx[3] = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) chunk_max(c, valid0);
+      }
+
+      for (int j = 0; j < w.total; ++j) {
+        const float m_new = fmaxf(m, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sc);
+        if (j == 0) {
+          m = m_new;
+        } else {
+          const bool need = m_new > m + 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            // O holds the accumulation up to tile j-1: wait for that PV, then rescale
+            mbar_wait(bar_o, (od + j - 1) & 1, 0x310 + s, p.dbg);
+            tc_fence_after();
+            const float alpha = need ? fast_exp2(m - m_new) : 1.0f;
+            if (need) m = m_new;
+            l *= alpha;
+            uint32_t ov[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              tmem_ld32(tO + c * 32, ov);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st32(tO + c * 32, ov);
+            }
+          }
+        }
+
+        // Software pipeline: while the MUFU works through chunk c of tile j, chunk c of S(j+1) — computed by the
+        // tensor core since S(j) was released — is pulled into the registers chunk c just vacated, and its row
+        // max is folded in one chunk later.  P(j) = exp2(S*scale - m) goes to TMEM in two halves.
+        const bool more = (j + 1 < w.total);
+        int valid_n = kBN;
+        if (more) valid_n = tile_valid(w, j + 1);
+        mx[0] = mx[1] = mx[2] = mx[3] = -INFINITY;
+        const uint64_t nm2 = pack_f2(-m, -m);
+        uint64_t ls[2] = {0ull, 0ull};
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t x2 =
+                ffma2(pack_f2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
+            float p0, p1;
+            if (poly_pair(i)) {
+              poly_exp2_x2(x2, p0, p1);
+            } else {
+              float x0, x1;
+              unpack_f2(x2, x0, x1);
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
+            ls[i & 1] = fadd2(ls[i & 1], pack_f2(p0, p1));
+            pk[(c & 1) * 16 + i] = pack2<kBF16>(p0, p1);
+          }
+          if (c & 1) {
+            if (c == 1 && j > 0) {
+              // P of this Q tile is read by the PV of tile j-1 until o_done completes
+              mbar_wait(bar_o, (od + j - 1) & 1, 0x311 + s, p.dbg);
+              tc_fence_after();
+            }
+            tmem_st32(tP + (c >> 1) * 32, pk);
+          }
+          if (more) {
+            if (c == 0) {
+              // S(j+1) was issued two tiles ahead; by now (32 exps later) it is normally complete
+              mbar_wait(bar_s, sph, 0x301 + s, p.dbg);
+              sph ^= 1;
+              tc_fence_after();
+            } else {
+              tc_wait_ld();
+              chunk_max(c - 1, valid_n);
+            }
+            tmem_ld32(tS + c * 32, sv[c]);
+          }
+        }
+        if (more) {
+          tc_wait_ld();
+          chunk_max(3, valid_n);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_f);
+        }
+        {
+          float a0, a1, b0, b1;
+          unpack_f2(ls[0], a0, a1);
+          unpack_f2(ls[1], b0, b1);
+          l += (a0 + a1) + (b0 + b1);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p);
+      }
+
+#else
       float m = -INFINITY;  // running max, already multiplied by scale*log2(e)
       float l = 0.f;
 
@@ -488,10 +607,15 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
           for (int i = 0; i < 16; ++i) {
             const uint64_t x2 =
                 ffma2(pack_f2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
-            float x0, x1;
-            unpack_f2(x2, x0, x1);
-            const float p0 = fast_exp2(x0);
-            const float p1 = fast_exp2(x1);
+            float p0, p1;
+            if (poly_pair(i)) {
+              poly_exp2_x2(x2, p0, p1);
+            } else {
+              float x0, x1;
+              unpack_f2(x2, x0, x1);
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
             ls[i & 1] = fadd2(ls[i & 1], pack_f2(p0, p1));
             pk[i] = pack2<kBF16>(p0, p1);
           }
@@ -509,6 +633,7 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         if (lane == 0) mbar_arrive(bar_p);
       }
 
+#endif
       // epilogue: wait for the last PV, normalise, store
       mbar_wait(bar_o, (od + w.total - 1) & 1, 0x320 + s, p.dbg);
       tc_fence_after();

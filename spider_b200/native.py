@@ -16,7 +16,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcsa_b200.so")
+# CSA_B200_LIB: developer knob to load an experimental build of the same ABI (kernel tuning sweeps); default in-tree
+LIB_PATH = os.environ.get("CSA_B200_LIB") or os.path.join(_HERE, "libcsa_b200.so")
 
 CSA_ABI_VERSION = 2
 CSA_DTYPE_F16 = 0
