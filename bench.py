@@ -261,7 +261,7 @@ def run_b200_arm(args):
     units_local = 2 * Fl
     if world > 1:
         from spider_b200.dist import FrameSharding
-        sharding = FrameSharding(Fl, dist.group.WORLD, dev)
+        sharding = FrameSharding(Fl, None, dev)
         units_local = sharding.local_batch
 
     # identical weights / masks on every rank: same seeds (the mask sample must agree across ranks)
@@ -282,6 +282,8 @@ def run_b200_arm(args):
     # the first step's masks, sampled like the driver does (Comic_Generation.py:376) in compact form
     host.mask1024, host.mask4096 = spider_b200.cal_attn_mask_xl(Fl + 1, Fl, args.sa, args.sa, H, W, device=str(dev),
                                                                 dtype=torch.float16)
+    if sharding is not None:
+        sharding.sync_masks(host.mask1024, host.mask4096)
     real_random = random.random
     random.random = lambda: 0.999   # gate forced open: every call takes the consistent branch (:98-103)
 

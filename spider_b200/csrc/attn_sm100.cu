@@ -25,6 +25,11 @@
 #define CSA_SOFTMAX_PIPE 0
 #endif
 // How many of every 16 element pairs take the polynomial exp2 (FMA/ALU pipes) instead of MUFU.EX2.
+// Threads per query row in the softmax: 1 (a thread owns a 128-column score row) or 2 (64 columns each, row max and
+// row sum exchanged through shared memory) — more warps per SM sub-partition to hide the ALU/MUFU latencies.
+#ifndef CSA_ROW_SPLIT
+#define CSA_ROW_SPLIT 1
+#endif
 #ifndef CSA_POLY_PAIRS
 #define CSA_POLY_PAIRS 0
 #endif
@@ -37,9 +42,17 @@ constexpr int kHD = 64;   // head dim
 constexpr int kTileBytes = kBN * kHD * 2;
 constexpr int kKStages = 4;
 constexpr int kVStages = 4;
+#if CSA_ROW_SPLIT == 2
+// two threads per query row (64 score columns each): 16 softmax warps = 4 per SM sub-partition
+constexpr int kThreads = 128 + 512;
+constexpr int kRegsCtl = 64;       // launch bound 96/thread: (96-64)*128 == (104-96)*512
+constexpr int kRegsSoftmax = 104;
+#else
 constexpr int kThreads = 384;
 constexpr int kRegsCtl = 88;       // producer / MMA / allocator warps after setmaxnreg.dec
-constexpr int kRegsSoftmax = 208;  // softmax warps after setmaxnreg.inc: (168-56)*128 == (224-168)*256
+constexpr int kRegsSoftmax = 208;  // softmax warps after setmaxnreg.inc: (168-88)*128 == (208-168)*256
+#endif
+constexpr int kSoftmaxWarpsPerTile = (kThreads - 128) / 64;  // arrivals on s_free / p_ready per Q tile
 
 // TMEM column map (fp32 columns)
 constexpr uint32_t kColS = 0;    // S0 at 0, S1 at 128
@@ -60,6 +73,8 @@ struct __align__(1024) AttnSmem {
   uint64_t v_full[kVStages], v_empty[kVStages];
   uint64_t s_full[2], s_free[2], p_ready[2], o_done[2];
   uint32_t tmem_base;
+  float xch_max[2][2][2][kBM];  // [Q tile][tile parity][column half][row]: partial row maxima (row split only)
+  float xch_sum[2][2][kBM];     // [Q tile][column half][row]: partial row sums at the end of a unit
 };
 
 struct AttnKernelParams {
@@ -191,8 +206,8 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       mbar_init(smem_u32(&sm.q_full[i]), 1);
       mbar_init(smem_u32(&sm.q_empty[i]), 1);
       mbar_init(smem_u32(&sm.s_full[i]), 1);
-      mbar_init(smem_u32(&sm.s_free[i]), kBM / 32);
-      mbar_init(smem_u32(&sm.p_ready[i]), kBM / 32);
+      mbar_init(smem_u32(&sm.s_free[i]), kSoftmaxWarpsPerTile);
+      mbar_init(smem_u32(&sm.p_ready[i]), kSoftmaxWarpsPerTile);
       mbar_init(smem_u32(&sm.o_done[i]), 1);
     }
     for (int i = 0; i < kKStages; ++i) {
@@ -375,6 +390,164 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
     }
   } else if (warp == 2) {
     setmaxnreg_dec<kRegsCtl>();
+#if CSA_ROW_SPLIT == 2
+  } else {
+    // =========================================================================================== softmax (2 thr/row)
+    setmaxnreg_inc<kRegsSoftmax>();
+    const int sw = warp - 4;                    // 0..15
+    const int quarter = sw & 3;                 // TMEM lane quarter (== warp % 4)
+    const int s = (sw >> 2) & 1;                // Q tile
+    const int half = sw >> 3;                   // which 64 score columns / 32 output columns of the row
+    const int row = (quarter << 5) | lane;      // query row inside the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(quarter << 5) << 16;
+    const uint32_t tS = tmem + lane_base + kColS + s * kBN + half * (kBN / 2);
+    const uint32_t tO = tmem + lane_base + kColO + s * kHD + half * (kHD / 2);
+    const uint32_t tP = tmem + lane_base + kColP + s * (kBN / 2) + half * (kBN / 4);
+    const uint32_t bar_s = smem_u32(&sm.s_full[s]);
+    const uint32_t bar_f = smem_u32(&sm.s_free[s]);
+    const uint32_t bar_p = smem_u32(&sm.p_ready[s]);
+    const uint32_t bar_o = smem_u32(&sm.o_done[s]);
+    const int pair_bar = 1 + s * 4 + quarter;   // named barrier shared by the two warps that own these 32 rows
+    const float sc = p.scale_log2;
+    const uint64_t sc2 = pack_f2(sc, sc);
+    uint32_t sph = 0;
+    uint32_t od = 0;  // PV completions on o_done[s] before the current unit
+
+    if (lane == 0) mbar_arrive(bar_f);  // S is free before the first QK of the kernel
+
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const Unit w = decode_unit(p, u);
+      const int q_in_frame = w.qp * (2 * kBM) + s * kBM + row;
+      const bool row_ok = q_in_frame < p.n_q;
+      uint4* optr = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
+                                             static_cast<int64_t>(w.q_row0 + s * kBM + row) * p.o_ld + w.h * kHD +
+                                             half * (kHD / 2));
+      if (w.total == 0) {
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) optr[i] = make_uint4(0, 0, 0, 0);
+        }
+        continue;
+      }
+      float m = -INFINITY;  // running max of the WHOLE row, already multiplied by scale*log2(e)
+      float l = 0.f;        // running sum of this thread's 64 columns
+
+      for (int j = 0; j < w.total; ++j) {
+        mbar_wait(bar_s, sph, 0x300 + s, p.dbg);
+        sph ^= 1;
+        tc_fence_after();
+        uint32_t sv[2][32];
+        tmem_ld32(tS + 0, sv[0]);
+        tmem_ld32(tS + 32, sv[1]);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_f);  // this warp's share of S is in registers
+
+        const int valid = tile_valid(w, j) - half * (kBN / 2);
+        if (valid < kBN / 2) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2)
+            mx[(i >> 1) & 3] = fmax3(mx[(i >> 1) & 3], __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+        const float mine = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        // exchange the partial maxima with the thread that owns the other 64 columns of this row
+        sm.xch_max[s][j & 1][half][row] = mine;
+        named_bar_sync(pair_bar, 64);
+        const float other = sm.xch_max[s][j & 1][half ^ 1][row];
+        const float m_new = fmaxf(m, fmaxf(mine, other) * sc);
+
+        if (j == 0) {
+          m = m_new;
+        } else {
+          // P and O of this Q tile are still being read by the PV of tile j-1 until o_done completes
+          mbar_wait(bar_o, (od + j - 1) & 1, 0x310 + s, p.dbg);
+          tc_fence_after();
+          const bool need = m_new > m + 8.0f;  // identical in both threads of the row
+          if (__any_sync(0xffffffffu, need)) {
+            const float alpha = need ? fast_exp2(m - m_new) : 1.0f;
+            if (need) m = m_new;
+            l *= alpha;
+            uint32_t ov[32];
+            tmem_ld32(tO, ov);  // this thread's 32 output columns
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st32(tO, ov);
+          }
+        }
+
+        const uint64_t nm2 = pack_f2(-m, -m);
+        uint64_t ls[2] = {0ull, 0ull};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t x2 =
+                ffma2(pack_f2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
+            float p0, p1;
+            if (poly_pair(i)) {
+              poly_exp2_x2(x2, p0, p1);
+            } else {
+              float x0, x1;
+              unpack_f2(x2, x0, x1);
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
+            ls[i & 1] = fadd2(ls[i & 1], pack_f2(p0, p1));
+            pk[i] = pack2<kBF16>(p0, p1);
+          }
+          tmem_st16(tP + c * 16, pk);
+        }
+        {
+          float a0, a1, b0, b1;
+          unpack_f2(ls[0], a0, a1);
+          unpack_f2(ls[1], b0, b1);
+          l += (a0 + a1) + (b0 + b1);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p);
+      }
+
+      // epilogue: wait for the last PV, add the two partial row sums, normalise and store this thread's 32 columns
+      mbar_wait(bar_o, (od + w.total - 1) & 1, 0x320 + s, p.dbg);
+      tc_fence_after();
+      od += w.total;
+      sm.xch_sum[s][half][row] = l;
+      named_bar_sync(pair_bar, 64);
+      const float inv = 1.0f / (l + sm.xch_sum[s][half ^ 1][row]);
+      {
+        uint32_t ov[32];
+        tmem_ld32(tO, ov);
+        tc_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 v4;
+            v4.x = pack2<kBF16>(__uint_as_float(ov[8 * i + 0]) * inv, __uint_as_float(ov[8 * i + 1]) * inv);
+            v4.y = pack2<kBF16>(__uint_as_float(ov[8 * i + 2]) * inv, __uint_as_float(ov[8 * i + 3]) * inv);
+            v4.z = pack2<kBF16>(__uint_as_float(ov[8 * i + 4]) * inv, __uint_as_float(ov[8 * i + 5]) * inv);
+            v4.w = pack2<kBF16>(__uint_as_float(ov[8 * i + 6]) * inv, __uint_as_float(ov[8 * i + 7]) * inv);
+            optr[i] = v4;
+          }
+        }
+      }
+      tc_fence_before();
+      named_bar_sync(pair_bar, 64);  // xch_sum may be rewritten by the next unit only after both threads read it
+    }
+  }
+#else
   } else {
     // =========================================================================================== softmax
     setmaxnreg_inc<kRegsSoftmax>();
@@ -659,6 +832,7 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       tc_fence_before();
     }
   }
+#endif
 
   __syncthreads();
   if (warp == 2) {

@@ -172,7 +172,7 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
         entry: Optional[BankEntry] = None
         if write:
             # :87-89 — keep what the read passes need.  K/V are this call's projection outputs (zero-copy).
-            if B < Fl:
+            if self.dist is None and B < Fl:
                 raise ValueError(f"write pass needs at least id_length={Fl} frames, got batch {B}")
             keep_hidden = self.bank_store in ("hidden", "both")
             keep_kv = self.bank_store in ("kv", "both")
@@ -181,6 +181,9 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                               k if keep_kv else None, v if keep_kv else None)
             self.id_bank[cur_step] = entry
         else:
+            if self.dist is not None:
+                raise NotImplementedError("read passes are not sharded: run them on a rank that holds the whole "
+                                          "id_bank (spider_b200/dist.py)")
             entry = self.id_bank[cur_step]   # KeyError for a step the write pass never reached (:92)
             if B != 2:
                 raise ValueError(f"read pass expects batch 2 (uncond, cond), got {B}")
@@ -199,8 +202,10 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                 branch = "consistent"
                 cm = self._compact_mask(h, N)
                 if write:
-                    if B != 2 * Fl:
-                        raise ValueError(f"consistent write pass expects batch 2*id_length={2 * Fl}, got {B} "
+                    want_b = 2 * Fl if self.dist is None else self.dist.local_batch
+                    if B != want_b:
+                        raise ValueError(f"consistent write pass expects batch 2*id_length={2 * Fl}"
+                                         f"{'' if self.dist is None else f' sharded to {want_b} per rank'}, got {B} "
                                          "(the reference fails with a mask shape error here)")
                     self._attn_write(q, k, v, o, N, heads, cm)
                 else:
@@ -227,6 +232,8 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
             h.mask1024, h.mask4096 = _masks.cal_attn_mask_xl(
                 self.total_length, self.id_length, h.sa32, h.sa64, h.height, h.width,
                 device=self.device, dtype=self.dtype)
+            if self.dist is not None:
+                self.dist.sync_masks(h.mask1024, h.mask4096)   # every rank must compact the same sample vector
         return out
 
     # ------------------------------------------------------------------------------------------------ branches

@@ -1,0 +1,109 @@
+"""CPU test doubles that follow the *semantics* of the C ABI (include/csa_b200.h) with plain torch, so that host-side
+logic that strings several native calls together (spider_b200/dist.py) can be exercised without a GPU.  Test
+infrastructure only: nothing under spider_b200/ imports this, and the GPU parity tests never use it."""
+import torch
+
+from oracle import reference_port as rp
+
+TILE = 128
+
+
+def idx_stride_for(n_cols):
+    return (n_cols + TILE - 1) // TILE * TILE
+
+
+def compact_rows(mask_rows, n_rows, n_cols, row_stride, block_n=0, limit_cols=0, idx=None, counts=None):
+    flat = mask_rows.reshape(-1).to(torch.uint8)
+    stride = idx_stride_for(n_cols)
+    idx = torch.zeros((n_rows, stride), dtype=torch.int32)
+    counts = torch.zeros((n_rows,), dtype=torch.int32)
+    for r in range(n_rows):
+        row = flat[r * row_stride:r * row_stride + n_cols].bool().clone()
+        if block_n > 0:
+            row[limit_cols:] = False
+            row[r * block_n:(r + 1) * block_n] = True
+        nz = torch.nonzero(row)[:, 0].int()
+        idx[r, :nz.numel()] = nz
+        counts[r] = nz.numel()
+    return idx, counts
+
+
+def sample_ranges(s_idx, s_count, block_n, n_frames):
+    c = int(s_count.item())
+    S = s_idx.reshape(-1)[:c].long()
+    out = torch.zeros((n_frames + 1, 4), dtype=torch.int32)
+    for f in range(n_frames):
+        lo = int(torch.searchsorted(S, torch.tensor(f * block_n)))
+        hi = int(torch.searchsorted(S, torch.tensor((f + 1) * block_n)))
+        out[f] = torch.tensor([0, lo, hi, c - hi], dtype=torch.int32)
+    out[n_frames] = torch.tensor([0, c, 0, 0], dtype=torch.int32)
+    return out
+
+
+def gather_rows(src, idx, max_rows, row_base=0, count=None, count_adjust=0, out=None):
+    n = max_rows if count is None else min(max_rows, int(count.item()) + count_adjust)
+    if out is None:
+        out = torch.empty((max_rows, src.shape[1]), dtype=src.dtype)
+    out[:n] = src[row_base + idx[:n].long()]
+    return out
+
+
+def gather_kv(k, v, group_rows, n_groups, s_idx, s_count, max_rows):
+    c = min(int(s_count.item()), max_rows)
+    cap = max_rows + TILE
+    s_idx = s_idx.reshape(-1)
+    # rows beyond the zero tail are "undefined" in the ABI: poison them so that a reader of them is caught
+    k_s = torch.full((n_groups * cap, k.shape[1]), float("nan"), dtype=k.dtype)
+    v_s = torch.full((n_groups * cap, k.shape[1]), float("nan"), dtype=k.dtype)
+    for g in range(n_groups):
+        k_s[g * cap:g * cap + c] = k[g * group_rows + s_idx[:c].long()]
+        v_s[g * cap:g * cap + c] = v[g * group_rows + s_idx[:c].long()]
+        k_s[g * cap + c:min((g + 1) * cap, g * cap + c + TILE)] = 0
+        v_s[g * cap + c:min((g + 1) * cap, g * cap + c + TILE)] = 0
+    return k_s, v_s, cap
+
+
+def attn_fwd(q, o, *, heads, n_groups, n_frames, n_q, k_a=None, v_a=None, a_group_rows=0, k_b=None, v_b=None,
+             b_group_rows=0, idx=None, counts=None, list_base=-1, list_step=0, g_adjust=0, ca=(0, 0, 0),
+             cb=(0, 0, 0), scale=None, max_ctas=0, ranges=None, range_base=0, range_step=0):
+    C = q.shape[1]
+    for g in range(n_groups):
+        for f in range(n_frames):
+            ks, vs = [], []
+            if list_base >= 0:
+                li = list_base + f * list_step
+                n = max(0, int(counts[li]) + g_adjust)
+                rows = g * a_group_rows + idx[li, :n].long()
+                ks.append(k_a[rows]); vs.append(v_a[rows])
+            if ranges is not None:
+                r = ranges[range_base + f * range_step].tolist()
+                for st, ln in ((r[0], r[1]), (r[2], r[3])):
+                    if ln > 0:
+                        ks.append(k_a[g * a_group_rows + st:g * a_group_rows + st + ln])
+                        vs.append(v_a[g * a_group_rows + st:g * a_group_rows + st + ln])
+            elif ca[2] > 0:
+                st = g * a_group_rows + ca[0] + f * ca[1]
+                ks.append(k_a[st:st + ca[2]]); vs.append(v_a[st:st + ca[2]])
+            if cb[2] > 0:
+                st = g * b_group_rows + cb[0] + f * cb[1]
+                ks.append(k_b[st:st + cb[2]]); vs.append(v_b[st:st + cb[2]])
+            kk, vv = torch.cat(ks).float(), torch.cat(vs).float()
+            assert torch.isfinite(kk).all() and torch.isfinite(vv).all(), "attention read an undefined K/V row"
+            qs = slice((g * n_frames + f) * n_q, (g * n_frames + f + 1) * n_q)
+            keys = [torch.arange(kk.shape[0], dtype=torch.int32)]
+            out = rp.gathered_attention(q[qs].float()[None], kk[None], vv[None], keys, heads)[0]
+            o[qs] = out.to(o.dtype)
+    return o
+
+
+def install(monkeypatch_or_none, native, processor_cls=None):
+    """Replace the native entry points by the emulations (monkeypatch fixture, or plain setattr when None)."""
+    pairs = dict(compact_rows=compact_rows, sample_ranges=sample_ranges, gather_rows=gather_rows,
+                 gather_kv=gather_kv, attn_fwd=attn_fwd)
+    for name, fn in pairs.items():
+        if monkeypatch_or_none is None:
+            setattr(native, name, fn)
+        else:
+            monkeypatch_or_none.setattr(native, name, fn)
+    if processor_cls is not None:
+        processor_cls._check_input = staticmethod(lambda x: None)
