@@ -175,6 +175,37 @@ __device__ __forceinline__ void locate_tile(const Unit& w, int t, int& seg, int&
   }
 }
 
+// Walks the key tiles of a unit in order (gathered list, A run 1, A run 2, B run) and yields the number of valid
+// keys of each: a few integer ops per tile instead of re-deriving the segment from the tile index.
+struct TileWalker {
+  int l1, l2, l3;  // lengths of the segments after the current one
+  int rem;         // keys left in the current segment
+  __device__ __forceinline__ void skip_empty() {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (rem <= 0) {
+        rem = l1;
+        l1 = l2;
+        l2 = l3;
+        l3 = 0;
+      }
+    }
+  }
+  __device__ __forceinline__ void init(const Unit& w) {
+    rem = w.ng;
+    l1 = w.seg_len[0];
+    l2 = w.seg_len[1];
+    l3 = w.seg_len[2];
+    skip_empty();
+  }
+  __device__ __forceinline__ int next() {
+    const int v = rem < kBN ? rem : kBN;
+    rem -= kBN;
+    skip_empty();
+    return v;
+  }
+};
+
 // number of valid keys in tile t of the unit
 __device__ __forceinline__ int tile_valid(const Unit& w, int t) {
   int seg, local;
@@ -191,6 +222,10 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // 32-bit shared-window address of the (aligned) storage; every barrier / tile address below is sb + constant, so
+  // no generic->shared conversion is redone inside the loops
+  const uint32_t sb = smem_u32(&sm);
+#define SB(field) (sb + static_cast<uint32_t>(offsetof(AttnSmem, field)))
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_q);
@@ -203,25 +238,25 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&sm.q_full[i]), 1);
-      mbar_init(smem_u32(&sm.q_empty[i]), 1);
-      mbar_init(smem_u32(&sm.s_full[i]), 1);
-      mbar_init(smem_u32(&sm.s_free[i]), kSoftmaxWarpsPerTile);
-      mbar_init(smem_u32(&sm.p_ready[i]), kSoftmaxWarpsPerTile);
-      mbar_init(smem_u32(&sm.o_done[i]), 1);
+      mbar_init((SB(q_full) + 8u * (i)), 1);
+      mbar_init((SB(q_empty) + 8u * (i)), 1);
+      mbar_init((SB(s_full) + 8u * (i)), 1);
+      mbar_init((SB(s_free) + 8u * (i)), kSoftmaxWarpsPerTile);
+      mbar_init((SB(p_ready) + 8u * (i)), kSoftmaxWarpsPerTile);
+      mbar_init((SB(o_done) + 8u * (i)), 1);
     }
     for (int i = 0; i < kKStages; ++i) {
-      mbar_init(smem_u32(&sm.k_full[i]), 1);
-      mbar_init(smem_u32(&sm.k_empty[i]), 2);  // one commit per MMA stream
+      mbar_init((SB(k_full) + 8u * (i)), 1);
+      mbar_init((SB(k_empty) + 8u * (i)), 2);  // one commit per MMA stream
     }
     for (int i = 0; i < kVStages; ++i) {
-      mbar_init(smem_u32(&sm.v_full[i]), 1);
-      mbar_init(smem_u32(&sm.v_empty[i]), 2);
+      mbar_init((SB(v_full) + 8u * (i)), 1);
+      mbar_init((SB(v_empty) + 8u * (i)), 2);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc<512>(smem_u32(&sm.tmem_base));
+    tmem_alloc<512>(SB(tmem_base));
   }
   tc_fence_before();
   __syncthreads();
@@ -241,9 +276,9 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       const int col = w.h * kHD;
       if (lane == 0) {
         for (int s = 0; s < 2; ++s) {
-          mbar_wait(smem_u32(&sm.q_empty[s]), qph ^ 1, 0x100 + s, p.dbg);
-          mbar_arrive_expect_tx(smem_u32(&sm.q_full[s]), kTileBytes);
-          tma_load_2d(&p.tm_q, smem_u32(sm.q[s]), smem_u32(&sm.q_full[s]), col, w.q_row0 + s * kBM);
+          mbar_wait((SB(q_empty) + 8u * (s)), qph ^ 1, 0x100 + s, p.dbg);
+          mbar_arrive_expect_tx((SB(q_full) + 8u * (s)), kTileBytes);
+          tma_load_2d(&p.tm_q, (SB(q) + static_cast<uint32_t>(kTileBytes) * (s)), (SB(q_full) + 8u * (s)), col, w.q_row0 + s * kBM);
         }
       }
       qph ^= 1;
@@ -294,26 +329,26 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         }
         // ---- K
         if (lane == 0) {
-          mbar_wait(smem_u32(&sm.k_empty[ks]), kph ^ 1, 0x110, p.dbg);
-          mbar_arrive_expect_tx(smem_u32(&sm.k_full[ks]), kTileBytes);
+          mbar_wait((SB(k_empty) + 8u * (ks)), kph ^ 1, 0x110, p.dbg);
+          mbar_arrive_expect_tx((SB(k_full) + 8u * (ks)), kTileBytes);
         }
         __syncwarp();
         if (gather) {
-          tma_gather4(mk, smem_u32(sm.k[ks]) + lane * 512, smem_u32(&sm.k_full[ks]), col, iv.x, iv.y, iv.z, iv.w);
+          tma_gather4(mk, (SB(k) + static_cast<uint32_t>(kTileBytes) * (ks)) + lane * 512, (SB(k_full) + 8u * (ks)), col, iv.x, iv.y, iv.z, iv.w);
         } else if (lane == 0) {
-          tma_load_2d(mk, smem_u32(sm.k[ks]), smem_u32(&sm.k_full[ks]), col, row0);
+          tma_load_2d(mk, (SB(k) + static_cast<uint32_t>(kTileBytes) * (ks)), (SB(k_full) + 8u * (ks)), col, row0);
         }
         if (++ks == kKStages) { ks = 0; kph ^= 1; }
         // ---- V
         if (lane == 0) {
-          mbar_wait(smem_u32(&sm.v_empty[vs]), vph ^ 1, 0x120, p.dbg);
-          mbar_arrive_expect_tx(smem_u32(&sm.v_full[vs]), kTileBytes);
+          mbar_wait((SB(v_empty) + 8u * (vs)), vph ^ 1, 0x120, p.dbg);
+          mbar_arrive_expect_tx((SB(v_full) + 8u * (vs)), kTileBytes);
         }
         __syncwarp();
         if (gather) {
-          tma_gather4(mv, smem_u32(sm.v[vs]) + lane * 512, smem_u32(&sm.v_full[vs]), col, iv.x, iv.y, iv.z, iv.w);
+          tma_gather4(mv, (SB(v) + static_cast<uint32_t>(kTileBytes) * (vs)) + lane * 512, (SB(v_full) + 8u * (vs)), col, iv.x, iv.y, iv.z, iv.w);
         } else if (lane == 0) {
-          tma_load_2d(mv, smem_u32(sm.v[vs]), smem_u32(&sm.v_full[vs]), col, row0);
+          tma_load_2d(mv, (SB(v) + static_cast<uint32_t>(kTileBytes) * (vs)), (SB(v_full) + 8u * (vs)), col, row0);
         }
         if (++vs == kVStages) { vs = 0; vph ^= 1; }
       }
@@ -334,25 +369,25 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       const uint32_t tS = tmem + kColS + s * kBN;
       const uint32_t tO = tmem + kColO + s * kHD;
       const uint32_t tP = tmem + kColP + s * (kBN / 2);
-      const uint32_t bar_qf = smem_u32(&sm.q_full[s]), bar_qe = smem_u32(&sm.q_empty[s]);
-      const uint32_t bar_sf = smem_u32(&sm.s_full[s]), bar_fr = smem_u32(&sm.s_free[s]);
-      const uint32_t bar_pr = smem_u32(&sm.p_ready[s]), bar_od = smem_u32(&sm.o_done[s]);
-      const uint64_t dq = make_sw128_desc(smem_u32(sm.q[s]));
+      const uint32_t bar_qf = (SB(q_full) + 8u * (s)), bar_qe = (SB(q_empty) + 8u * (s));
+      const uint32_t bar_sf = (SB(s_full) + 8u * (s)), bar_fr = (SB(s_free) + 8u * (s));
+      const uint32_t bar_pr = (SB(p_ready) + 8u * (s)), bar_od = (SB(o_done) + 8u * (s));
+      const uint64_t dq = make_sw128_desc((SB(q) + static_cast<uint32_t>(kTileBytes) * (s)));
 
       // S = Q K^T for the K tile in stage `ks`; releases the stage and, for the unit's last tile, the Q tile
       auto qk_step = [&](bool last) {
-        mbar_wait(smem_u32(&sm.k_full[ks]), kph, 0x201 + s, p.dbg);
+        mbar_wait((SB(k_full) + 8u * (ks)), kph, 0x201 + s, p.dbg);
         mbar_wait(bar_fr, fph, 0x203 + s, p.dbg);  // softmax has pulled the previous S into registers
         fph ^= 1;
         tc_fence_after();
-        const uint64_t dk = make_sw128_desc(smem_u32(sm.k[ks]));
+        const uint64_t dk = make_sw128_desc((SB(k) + static_cast<uint32_t>(kTileBytes) * (ks)));
 #pragma unroll
         for (int kk = 0; kk < kHD / 16; ++kk) {
           // advance 16 elements (32 B) along the contraction dim inside the swizzled 128 B row
           mma_ss(tS, dq + kk * 2, dk + kk * 2, idesc_qk, kk > 0 ? 1u : 0u);
         }
         tc_commit(bar_sf);
-        tc_commit(smem_u32(&sm.k_empty[ks]));
+        tc_commit((SB(k_empty) + 8u * (ks)));
         if (last) tc_commit(bar_qe);
         if (++ks == kKStages) { ks = 0; kph ^= 1; }
       };
@@ -368,11 +403,11 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
 #if CSA_SOFTMAX_PIPE
           if (j + 2 < w.total) qk_step(j + 3 == w.total);  // F(j+1) and P(j) arrive together: scores first
 #endif
-          mbar_wait(smem_u32(&sm.v_full[vs]), vph, 0x210 + s, p.dbg);
+          mbar_wait((SB(v_full) + 8u * (vs)), vph, 0x210 + s, p.dbg);
           mbar_wait(bar_pr, pph, 0x212 + s, p.dbg);
           pph ^= 1;
           tc_fence_after();
-          const uint64_t dv = make_sw128_desc(smem_u32(sm.v[vs]));
+          const uint64_t dv = make_sw128_desc((SB(v) + static_cast<uint32_t>(kTileBytes) * (vs)));
 #pragma unroll
           for (int kk = 0; kk < kBN / 16; ++kk) {
             // 16 keys = 16 rows of 128 B = 2048 B along the contraction dim (MN-major B operand);
@@ -380,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
             mma_ts(tO, tP + kk * 8, dv + kk * (2048 >> 4), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
           }
           tc_commit(bar_od);
-          tc_commit(smem_u32(&sm.v_empty[vs]));
+          tc_commit((SB(v_empty) + 8u * (vs)));
           if (++vs == kVStages) { vs = 0; vph ^= 1; }
 #if !CSA_SOFTMAX_PIPE
           if (j + 2 < w.total) qk_step(j + 3 == w.total);  // F(j+1) arrives after P(j): PV first
@@ -403,10 +438,10 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
     const uint32_t tS = tmem + lane_base + kColS + s * kBN + half * (kBN / 2);
     const uint32_t tO = tmem + lane_base + kColO + s * kHD + half * (kHD / 2);
     const uint32_t tP = tmem + lane_base + kColP + s * (kBN / 2) + half * (kBN / 4);
-    const uint32_t bar_s = smem_u32(&sm.s_full[s]);
-    const uint32_t bar_f = smem_u32(&sm.s_free[s]);
-    const uint32_t bar_p = smem_u32(&sm.p_ready[s]);
-    const uint32_t bar_o = smem_u32(&sm.o_done[s]);
+    const uint32_t bar_s = (SB(s_full) + 8u * (s));
+    const uint32_t bar_f = (SB(s_free) + 8u * (s));
+    const uint32_t bar_p = (SB(p_ready) + 8u * (s));
+    const uint32_t bar_o = (SB(o_done) + 8u * (s));
     const int pair_bar = 1 + s * 4 + quarter;   // named barrier shared by the two warps that own these 32 rows
     const float sc = p.scale_log2;
     const uint64_t sc2 = pack_f2(sc, sc);
@@ -431,6 +466,8 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       }
       float m = -INFINITY;  // running max of the WHOLE row, already multiplied by scale*log2(e)
       float l = 0.f;        // running sum of this thread's 64 columns
+      TileWalker walk;
+      walk.init(w);
 
       for (int j = 0; j < w.total; ++j) {
         mbar_wait(bar_s, sph, 0x300 + s, p.dbg);
@@ -444,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_f);  // this warp's share of S is in registers
 
-        const int valid = tile_valid(w, j) - half * (kBN / 2);
+        const int valid = walk.next() - half * (kBN / 2);
         if (valid < kBN / 2) {
 #pragma unroll
           for (int c = 0; c < 2; ++c)
@@ -557,10 +594,10 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
     const uint32_t tS = tmem + lane_base + kColS + s * kBN;
     const uint32_t tO = tmem + lane_base + kColO + s * kHD;
     const uint32_t tP = tmem + lane_base + kColP + s * (kBN / 2);
-    const uint32_t bar_s = smem_u32(&sm.s_full[s]);
-    const uint32_t bar_f = smem_u32(&sm.s_free[s]);
-    const uint32_t bar_p = smem_u32(&sm.p_ready[s]);
-    const uint32_t bar_o = smem_u32(&sm.o_done[s]);
+    const uint32_t bar_s = (SB(s_full) + 8u * (s));
+    const uint32_t bar_f = (SB(s_free) + 8u * (s));
+    const uint32_t bar_p = (SB(p_ready) + 8u * (s));
+    const uint32_t bar_o = (SB(o_done) + 8u * (s));
     const float sc = p.scale_log2;
     const uint64_t sc2 = pack_f2(sc, sc);
     uint32_t sph = 0;
@@ -714,6 +751,8 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
 #else
       float m = -INFINITY;  // running max, already multiplied by scale*log2(e)
       float l = 0.f;
+      TileWalker walk;
+      walk.init(w);
 
       for (int j = 0; j < w.total; ++j) {
         mbar_wait(bar_s, sph, 0x300 + s, p.dbg);
@@ -730,7 +769,7 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_f);
 
-        const int valid = tile_valid(w, j);
+        const int valid = walk.next();
         if (valid < kBN) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
