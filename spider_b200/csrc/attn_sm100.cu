@@ -33,6 +33,13 @@
 #ifndef CSA_POLY_PAIRS
 #define CSA_POLY_PAIRS 0
 #endif
+// Exp-phase ping-pong: the two softmax warps that share an SM sub-partition (same TMEM lane quarter, Q tile 0 and
+// Q tile 1) hand a token back and forth through a pair of named barriers, so that one exponentiates (MUFU-bound)
+// while the other waits for its PV, pulls the next scores and takes the row max.  Without it the two Q-tile streams
+// run in phase (both start on the same K tile) and the MUFU idles whenever both are outside the exp phase.
+#ifndef CSA_PINGPONG
+#define CSA_PINGPONG 1
+#endif
 
 namespace csa {
 
@@ -602,6 +609,12 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
     const uint64_t sc2 = pack_f2(sc, sc);
     uint32_t sph = 0;
     uint32_t od = 0;  // PV completions on o_done[s] before the current unit
+#if CSA_PINGPONG
+    // named barriers 1..8: two per lane quarter, one per direction of the exp token (Q tile 0 holds it first)
+    const int tok_in = 1 + 2 * (warp & 3) + (s ^ 1);  // completed by the other Q tile's warp after its exp phase
+    const int tok_out = 1 + 2 * (warp & 3) + s;
+    bool have_token = (s == 0);
+#endif
 
     if (lane == 0) mbar_arrive(bar_f);  // S is free before the first QK of the kernel
 
@@ -812,6 +825,13 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         // P = exp2(S*scale - m) in chunks of 32 keys: FFMA2 -> MUFU.EX2 -> FADD2 row sum -> pack -> TMEM
         const uint64_t nm2 = pack_f2(-m, -m);
         uint64_t ls[2] = {0ull, 0ull};
+#if CSA_PINGPONG
+        if (have_token) {
+          have_token = false;
+        } else {
+          named_bar_sync(tok_in, 64);  // the other Q tile's warp on this sub-partition has issued its exponentials
+        }
+#endif
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
@@ -833,6 +853,9 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
           }
           tmem_st16(tP + c * 16, pk);
         }
+#if CSA_PINGPONG
+        named_bar_arrive(tok_out, 64);
+#endif
         {
           float a0, a1, b0, b1;
           unpack_f2(ls[0], a0, a1);
@@ -870,6 +893,10 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       }
       tc_fence_before();
     }
+#if CSA_PINGPONG && !CSA_SOFTMAX_PIPE
+    // Q tile 1's last hand-over has no taker: absorb it so that no barrier is left half-arrived at exit
+    if (s == 0 && !have_token) named_bar_sync(tok_in, 64);
+#endif
   }
 #endif
 

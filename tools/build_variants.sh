@@ -1,6 +1,6 @@
 #!/bin/bash
 # Builds tuning variants of libcsa_b200.so (same ABI, different -D knobs) into spider_b200/variants/.
-# usage: tools/build_variants.sh "PIPE POLY [SPLIT]" ...   e.g.  tools/build_variants.sh "0 0" "0 4 2" "1 4"
+# usage: tools/build_variants.sh "PIPE POLY [SPLIT [PINGPONG [EXTRA -D flags]]]" ...   e.g.  tools/build_variants.sh "0 0" "0 4 2" "1 4"
 set -e
 cd "$(dirname "$0")/../spider_b200/csrc"
 mkdir -p ../variants build
@@ -8,8 +8,10 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 for v in "$@"; do
   set -- $v
   split=${3:-1}
-  name="p$1_k$2_s$split"
-  nvcc $ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -DCSA_SOFTMAX_PIPE=$1 -DCSA_POLY_PAIRS=$2 -DCSA_ROW_SPLIT=$split -Xptxas -v \
+  pp=${4:-1}
+  extra=${5:-}
+  name="p$1_k$2_s${split}_g$pp$(echo "$extra" | tr -d ' =-' | tr 'A-Z' 'a-z')"
+  nvcc $ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -DCSA_SOFTMAX_PIPE=$1 -DCSA_POLY_PAIRS=$2 -DCSA_ROW_SPLIT=$split -DCSA_PINGPONG=$pp $extra -Xptxas -v \
     -c attn_sm100.cu -o build/attn_$name.o
   nvcc $ARCH -shared -o ../variants/libcsa_$name.so build/abi.o build/compact.o build/attn_$name.o -lcudart
   echo built $name
