@@ -59,6 +59,11 @@ int csa_device_supported(int device);
  * and returns 1; returns 0 if nothing is recorded.  Synchronises the device.  Debug aid only. */
 int csa_debug_stuck(uint32_t* out4_host);
 
+/* Timeline trace of the attention kernel (libraries built with -DCSA_TRACE=1 only; the shipped build returns
+ * CSA_E_BADARG): `dev_buffer` receives 4 x 8192 64-bit words {event id << 48 | SM clock} written by CTA 0.
+ * Pass NULL to switch tracing off.  Debug aid only (tools/trace_timeline.py). */
+int csa_debug_set_trace(void* dev_buffer);
+
 /*
  * Compact `n_rows` boolean rows of `n_cols` bytes each into ascending column index lists.
  *   mask        row r starts at mask + r*row_stride bytes; byte != 0 means "attend".  row_stride may be 0

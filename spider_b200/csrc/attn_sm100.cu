@@ -40,8 +40,53 @@
 #ifndef CSA_PINGPONG
 #define CSA_PINGPONG 1
 #endif
+// The token is handed over after this 32-key chunk (0..3) of the exp phase has been issued: 3 = strict alternation,
+// smaller = the two exp phases overlap at the seam, which keeps the MUFU queue full across the hand-over.
+#ifndef CSA_TOKEN_CHUNK
+#define CSA_TOKEN_CHUNK 3
+#endif
+// Early score load.  0: a tile's scores are read (tcgen05.ld) at the top of its iteration.  1: the registers of a
+// 32-key chunk are refilled with the next tile's scores as soon as the chunk's FFMA2s have consumed them (measured
+// slower: S(j+1) is then needed an exp phase earlier than the QK that produces it can deliver).  2: the next tile's
+// scores are read right after the last exponential is issued, under the P store drain and the p_ready hand-over.
+#ifndef CSA_EARLY_LD
+#define CSA_EARLY_LD 0
+#endif
+#ifndef CSA_DEFER_ODONE
+#define CSA_DEFER_ODONE 0
+#endif
+
+// Timeline trace (debug builds only, -DCSA_TRACE=1): lane 0 of a few warps of CTA 0 records (event, clock) pairs
+// into a device buffer set with csa_debug_set_trace(); tools/trace_timeline.py turns them into per-tile latencies.
+#ifndef CSA_TRACE
+#define CSA_TRACE 0
+#endif
 
 namespace csa {
+
+#if CSA_TRACE
+__device__ unsigned long long* g_trace = nullptr;
+constexpr int kTraceSlots = 4;       // softmax warp of Q tile 0 / 1 (lane quarter 0), MMA warp of Q tile 0 / 1
+constexpr int kTraceEvents = 8192;   // per slot
+struct Tracer {
+  unsigned long long* base;
+  uint32_t n;
+  __device__ __forceinline__ void init(int slot, bool on) {
+    base = (on && g_trace != nullptr && blockIdx.x == 0) ? g_trace + slot * kTraceEvents : nullptr;
+    n = 0;
+  }
+  __device__ __forceinline__ void ev(uint32_t id) {
+    if (base != nullptr && n < kTraceEvents) {
+      base[n++] = (static_cast<unsigned long long>(id) << 48) | (static_cast<unsigned long long>(clock64()) & 0xffffffffffffull);
+    }
+  }
+};
+#define TRACE_INIT(slot, on) Tracer tracer; tracer.init(slot, on)
+#define TRACE(id) tracer.ev(id)
+#else
+#define TRACE_INIT(slot, on)
+#define TRACE(id)
+#endif
 
 constexpr int kBM = 128;  // query rows per Q tile
 constexpr int kBN = 128;  // keys per K/V tile
@@ -367,8 +412,10 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
     // would serialise the two softmax warpgroups).  Per stream: QK(0), QK(1), then {QK(j+2), PV(j)} — the scores
     // run two tiles ahead of the PV so that S(j+1) is in TMEM while the softmax warps exponentiate tile j.
     setmaxnreg_dec<kRegsCtl>();
-    if (lane == 0) {
-      const int s = warp >> 1;  // 0 or 1
+    // The whole warp runs the control flow (so that descriptors, stage indices and phases are warp-uniform and live
+    // in uniform registers); one elected lane issues the tcgen05 instructions and their commits.
+    {
+      const int s = __shfl_sync(0xffffffffu, warp >> 1, 0);  // 0 or 1
       constexpr uint32_t idesc_qk = make_idesc(kBM, kBN, kBF16 ? 1 : 0, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(kBM, kHD, kBF16 ? 1 : 0, 0, 1);
       int ks = 0, vs = 0;
@@ -380,22 +427,29 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       const uint32_t bar_sf = (SB(s_full) + 8u * (s)), bar_fr = (SB(s_free) + 8u * (s));
       const uint32_t bar_pr = (SB(p_ready) + 8u * (s)), bar_od = (SB(o_done) + 8u * (s));
       const uint64_t dq = make_sw128_desc((SB(q) + static_cast<uint32_t>(kTileBytes) * (s)));
+      TRACE_INIT(2 + s, lane == 0);
 
       // S = Q K^T for the K tile in stage `ks`; releases the stage and, for the unit's last tile, the Q tile
       auto qk_step = [&](bool last) {
+        TRACE(20);
         mbar_wait((SB(k_full) + 8u * (ks)), kph, 0x201 + s, p.dbg);
+        TRACE(21);
         mbar_wait(bar_fr, fph, 0x203 + s, p.dbg);  // softmax has pulled the previous S into registers
         fph ^= 1;
         tc_fence_after();
+        TRACE(22);
         const uint64_t dk = make_sw128_desc((SB(k) + static_cast<uint32_t>(kTileBytes) * (ks)));
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < kHD / 16; ++kk) {
-          // advance 16 elements (32 B) along the contraction dim inside the swizzled 128 B row
-          mma_ss(tS, dq + kk * 2, dk + kk * 2, idesc_qk, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < kHD / 16; ++kk) {
+            // advance 16 elements (32 B) along the contraction dim inside the swizzled 128 B row
+            mma_ss(tS, dq + kk * 2, dk + kk * 2, idesc_qk, kk > 0 ? 1u : 0u);
+          }
+          tc_commit(bar_sf);
+          tc_commit((SB(k_empty) + 8u * (ks)));
+          if (last) tc_commit(bar_qe);
         }
-        tc_commit(bar_sf);
-        tc_commit((SB(k_empty) + 8u * (ks)));
-        if (last) tc_commit(bar_qe);
+        __syncwarp();
         if (++ks == kKStages) { ks = 0; kph ^= 1; }
       };
 
@@ -410,19 +464,26 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
 #if CSA_SOFTMAX_PIPE
           if (j + 2 < w.total) qk_step(j + 3 == w.total);  // F(j+1) and P(j) arrive together: scores first
 #endif
+          TRACE(23);
           mbar_wait((SB(v_full) + 8u * (vs)), vph, 0x210 + s, p.dbg);
+          TRACE(24);
           mbar_wait(bar_pr, pph, 0x212 + s, p.dbg);
           pph ^= 1;
           tc_fence_after();
+          TRACE(25);
           const uint64_t dv = make_sw128_desc((SB(v) + static_cast<uint32_t>(kTileBytes) * (vs)));
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < kBN / 16; ++kk) {
-            // 16 keys = 16 rows of 128 B = 2048 B along the contraction dim (MN-major B operand);
-            // 16 16-bit P values = 8 TMEM columns
-            mma_ts(tO, tP + kk * 8, dv + kk * (2048 >> 4), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < kBN / 16; ++kk) {
+              // 16 keys = 16 rows of 128 B = 2048 B along the contraction dim (MN-major B operand);
+              // 16 16-bit P values = 8 TMEM columns
+              mma_ts(tO, tP + kk * 8, dv + kk * (2048 >> 4), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+            }
+            tc_commit(bar_od);
+            tc_commit((SB(v_empty) + 8u * (vs)));
           }
-          tc_commit(bar_od);
-          tc_commit((SB(v_empty) + 8u * (vs)));
+          __syncwarp();
+          TRACE(26);
           if (++vs == kVStages) { vs = 0; vph ^= 1; }
 #if !CSA_SOFTMAX_PIPE
           if (j + 2 < w.total) qk_step(j + 3 == w.total);  // F(j+1) arrives after P(j): PV first
@@ -454,6 +515,12 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
     const uint64_t sc2 = pack_f2(sc, sc);
     uint32_t sph = 0;
     uint32_t od = 0;  // PV completions on o_done[s] before the current unit
+#if CSA_PINGPONG
+    // exp token between the two Q tiles, handed over by whole warpgroup pairs (named barriers 9 and 10)
+    const int tok_in = 9 + (s ^ 1);
+    const int tok_out = 9 + s;
+    bool have_token = (s == 0);
+#endif
 
     if (lane == 0) mbar_arrive(bar_f);  // S is free before the first QK of the kernel
 
@@ -529,8 +596,16 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
           }
         }
 
-        const uint64_t nm2 = pack_f2(-m, -m);
+        uint64_t nm2 = pack_f2(-m, -m);
         uint64_t ls[2] = {0ull, 0ull};
+#if CSA_PINGPONG
+        if (have_token) {
+          have_token = false;
+        } else {
+          named_bar_sync(tok_in, 512);
+        }
+        asm volatile("" : "+l"(nm2));  // every exponential depends on nm2: none may be hoisted above the token
+#endif
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t pk[16];
@@ -551,6 +626,9 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
             pk[i] = pack2<kBF16>(p0, p1);
           }
           tmem_st16(tP + c * 16, pk);
+#if CSA_PINGPONG
+          if (c == (CSA_TOKEN_CHUNK >= 2 ? 1 : 0)) named_bar_arrive(tok_out, 512);
+#endif
         }
         {
           float a0, a1, b0, b1;
@@ -590,6 +668,9 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       tc_fence_before();
       named_bar_sync(pair_bar, 64);  // xch_sum may be rewritten by the next unit only after both threads read it
     }
+#if CSA_PINGPONG
+    if (s == 0 && !have_token) named_bar_sync(tok_in, 512);  // absorb Q tile 1's last hand-over
+#endif
   }
 #else
   } else {
@@ -615,6 +696,7 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
     const int tok_out = 1 + 2 * (warp & 3) + s;
     bool have_token = (s == 0);
 #endif
+    TRACE_INIT(s, (warp & 3) == 0 && lane == 0);
 
     if (lane == 0) mbar_arrive(bar_f);  // S is free before the first QK of the kernel
 
@@ -624,6 +706,7 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       const bool row_ok = q_in_frame < p.n_q;
       uint4* optr = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
                                              static_cast<int64_t>(w.q_row0 + s * kBM + row) * p.o_ld + w.h * kHD);
+      TRACE(10);
       if (w.total == 0) {
         if (row_ok) {
 #pragma unroll
@@ -636,6 +719,8 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       float l = 0.f;
       uint32_t sv[4][32];  // the score row of the tile being exponentiated; refilled in place with the next tile's
       float mx[4];         // partial row maxima (unscaled) of the tile held in sv
+      TileWalker walk;
+      walk.init(w);
 
       // masks the keys beyond `valid` of chunk c and folds the chunk into the partial maxima
       auto chunk_max = [&](const int c, const int valid) {
@@ -662,7 +747,7 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_f);  // S may be overwritten with the next tile's scores
       {
-        const int valid0 = tile_valid(w, 0);
+        const int valid0 = walk.next();
         mx[0] = mx[1] = mx[2] = mx[3] = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 4; ++c) chunk_max(c, valid0);
@@ -670,139 +755,12 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
 
       for (int j = 0; j < w.total; ++j) {
         const float m_new = fmaxf(m, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sc);
+        TRACE(4);
+        // Everything the exp phase will wait for is checked before the token is taken (a token holder that stalls
+        // blocks both Q tiles): the PV of tile j-1 (it reads P and O of this Q tile) and the scores of tile j+1.
         if (j == 0) {
           m = m_new;
         } else {
-          const bool need = m_new > m + 8.0f;
-          if (__any_sync(0xffffffffu, need)) {
-            // O holds the accumulation up to tile j-1: wait for that PV, then rescale
-            mbar_wait(bar_o, (od + j - 1) & 1, 0x310 + s, p.dbg);
-            tc_fence_after();
-            const float alpha = need ? fast_exp2(m - m_new) : 1.0f;
-            if (need) m = m_new;
-            l *= alpha;
-            uint32_t ov[32];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              tmem_ld32(tO + c * 32, ov);
-              tc_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-              tmem_st32(tO + c * 32, ov);
-            }
-          }
-        }
-
-        // Software pipeline: while the MUFU works through chunk c of tile j, chunk c of S(j+1) — computed by the
-        // tensor core since S(j) was released — is pulled into the registers chunk c just vacated, and its row
-        // max is folded in one chunk later.  P(j) = exp2(S*scale - m) goes to TMEM in two halves.
-        const bool more = (j + 1 < w.total);
-        int valid_n = kBN;
-        if (more) valid_n = tile_valid(w, j + 1);
-        mx[0] = mx[1] = mx[2] = mx[3] = -INFINITY;
-        const uint64_t nm2 = pack_f2(-m, -m);
-        uint64_t ls[2] = {0ull, 0ull};
-        uint32_t pk[32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const uint64_t x2 =
-                ffma2(pack_f2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
-            float p0, p1;
-            if (poly_pair(i)) {
-              poly_exp2_x2(x2, p0, p1);
-            } else {
-              float x0, x1;
-              unpack_f2(x2, x0, x1);
-              p0 = fast_exp2(x0);
-              p1 = fast_exp2(x1);
-            }
-            ls[i & 1] = fadd2(ls[i & 1], pack_f2(p0, p1));
-            pk[(c & 1) * 16 + i] = pack2<kBF16>(p0, p1);
-          }
-          if (c & 1) {
-            if (c == 1 && j > 0) {
-              // P of this Q tile is read by the PV of tile j-1 until o_done completes
-              mbar_wait(bar_o, (od + j - 1) & 1, 0x311 + s, p.dbg);
-              tc_fence_after();
-            }
-            tmem_st32(tP + (c >> 1) * 32, pk);
-          }
-          if (more) {
-            if (c == 0) {
-              // S(j+1) was issued two tiles ahead; by now (32 exps later) it is normally complete
-              mbar_wait(bar_s, sph, 0x301 + s, p.dbg);
-              sph ^= 1;
-              tc_fence_after();
-            } else {
-              tc_wait_ld();
-              chunk_max(c - 1, valid_n);
-            }
-            tmem_ld32(tS + c * 32, sv[c]);
-          }
-        }
-        if (more) {
-          tc_wait_ld();
-          chunk_max(3, valid_n);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_f);
-        }
-        {
-          float a0, a1, b0, b1;
-          unpack_f2(ls[0], a0, a1);
-          unpack_f2(ls[1], b0, b1);
-          l += (a0 + a1) + (b0 + b1);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p);
-      }
-
-#else
-      float m = -INFINITY;  // running max, already multiplied by scale*log2(e)
-      float l = 0.f;
-      TileWalker walk;
-      walk.init(w);
-
-      for (int j = 0; j < w.total; ++j) {
-        mbar_wait(bar_s, sph, 0x300 + s, p.dbg);
-        sph ^= 1;
-        tc_fence_after();
-        uint32_t sv[4][32];
-        tmem_ld32(tS + 0, sv[0]);
-        tmem_ld32(tS + 32, sv[1]);
-        tmem_ld32(tS + 64, sv[2]);
-        tmem_ld32(tS + 96, sv[3]);
-        tc_wait_ld();
-        // the score row now lives in registers: let the tensor core overwrite S with the next tile's scores
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_f);
-
-        const int valid = walk.next();
-        if (valid < kBN) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
-        }
-        // row max: 4 independent chains of 3-input max
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            mx[(i >> 1) & 3] = fmax3(mx[(i >> 1) & 3], __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
-        const float m_new = fmaxf(m, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sc);
-
-        if (j == 0) {
-          m = m_new;
-        } else {
-          // P and O of this Q tile are still being read by the PV of tile j-1 until o_done completes
           mbar_wait(bar_o, (od + j - 1) & 1, 0x310 + s, p.dbg);
           tc_fence_after();
           const bool need = m_new > m + 8.0f;
@@ -821,9 +779,21 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
             }
           }
         }
+        const bool more = (j + 1 < w.total);
+        int valid_n = kBN;
+        if (more) {
+          valid_n = walk.next();
+          mbar_wait(bar_s, sph, 0x301 + s, p.dbg);
+          sph ^= 1;
+          tc_fence_after();
+        }
+        TRACE(5);
 
-        // P = exp2(S*scale - m) in chunks of 32 keys: FFMA2 -> MUFU.EX2 -> FADD2 row sum -> pack -> TMEM
-        const uint64_t nm2 = pack_f2(-m, -m);
+        // Software pipeline: while the MUFU works through chunk c of tile j, chunk c of S(j+1) — computed by the
+        // tensor core since S(j) was released — is pulled into the registers chunk c just vacated, and its row
+        // max is folded in one chunk later.
+        mx[0] = mx[1] = mx[2] = mx[3] = -INFINITY;
+        uint64_t nm2 = pack_f2(-m, -m);
         uint64_t ls[2] = {0ull, 0ull};
 #if CSA_PINGPONG
         if (have_token) {
@@ -831,20 +801,31 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         } else {
           named_bar_sync(tok_in, 64);  // the other Q tile's warp on this sub-partition has issued its exponentials
         }
+        asm volatile("" : "+l"(nm2));  // every exponential depends on nm2: none may be hoisted above the token
 #endif
+        TRACE(6);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          uint64_t xs[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            xs[i] = ffma2(pack_f2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
+          if (more) {
+            if (c > 0) {
+              tc_wait_ld();
+              chunk_max(c - 1, valid_n);
+            }
+            tmem_ld32(tS + c * 32, sv[c]);  // the chunk's scores are consumed: refill with the next tile's
+          }
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const uint64_t x2 =
-                ffma2(pack_f2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
             float p0, p1;
             if (poly_pair(i)) {
-              poly_exp2_x2(x2, p0, p1);
+              poly_exp2_x2(xs[i], p0, p1);
             } else {
               float x0, x1;
-              unpack_f2(x2, x0, x1);
+              unpack_f2(xs[i], x0, x1);
               p0 = fast_exp2(x0);
               p1 = fast_exp2(x1);
             }
@@ -852,10 +833,18 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
             pk[i] = pack2<kBF16>(p0, p1);
           }
           tmem_st16(tP + c * 16, pk);
-        }
 #if CSA_PINGPONG
-        named_bar_arrive(tok_out, 64);
+          if (c == CSA_TOKEN_CHUNK) named_bar_arrive(tok_out, 64);  // the other Q tile may start its exponentials
 #endif
+        }
+        TRACE(7);
+        if (more) {
+          tc_wait_ld();
+          chunk_max(3, valid_n);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_f);
+        }
         {
           float a0, a1, b0, b1;
           unpack_f2(ls[0], a0, a1);
@@ -866,12 +855,204 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p);
+        TRACE(8);
+      }
+
+#else
+      float m = -INFINITY;  // running max, already multiplied by scale*log2(e)
+      float l = 0.f;
+      TileWalker walk;
+      walk.init(w);
+      uint32_t sv[4][32];  // the score row of the current tile (a thread owns a whole 128-key row)
+
+#if CSA_EARLY_LD
+      // scores of the unit's first tile; later tiles are pulled during the exp phase of their predecessor
+      mbar_wait(bar_s, sph, 0x300 + s, p.dbg);
+      sph ^= 1;
+      tc_fence_after();
+      tmem_ld32(tS + 0, sv[0]);
+      tmem_ld32(tS + 32, sv[1]);
+      tmem_ld32(tS + 64, sv[2]);
+      tmem_ld32(tS + 96, sv[3]);
+      tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_f);
+#endif
+
+      for (int j = 0; j < w.total; ++j) {
+#if !CSA_EARLY_LD
+        TRACE(1);
+        mbar_wait(bar_s, sph, 0x300 + s, p.dbg);
+        sph ^= 1;
+        tc_fence_after();
+        TRACE(2);
+        tmem_ld32(tS + 0, sv[0]);
+        tmem_ld32(tS + 32, sv[1]);
+        tmem_ld32(tS + 64, sv[2]);
+        tmem_ld32(tS + 96, sv[3]);
+        tc_wait_ld();
+        // the score row now lives in registers: let the tensor core overwrite S with the next tile's scores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_f);
+        TRACE(3);
+#endif
+
+        const int valid = walk.next();
+        if (valid < kBN) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
+        }
+        // row max: 4 independent chains of 3-input max
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2)
+            mx[(i >> 1) & 3] = fmax3(mx[(i >> 1) & 3], __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+        const float m_new = fmaxf(m, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sc);
+#if CSA_TRACE
+        asm volatile("" ::"f"(m_new));
+        TRACE(4);
+#endif
+
+        // P and O of this Q tile are still being read by the PV of tile j-1 until o_done completes.
+        // CSA_DEFER_ODONE=1 moves the wait of the common case (no rescale of O) to just before the first P store;
+        // measured slower with the exp token: a token holder that stalls blocks both Q tiles.
+        bool pv_pending = (j > 0);
+        if (j == 0) {
+          m = m_new;
+        } else {
+          const bool need = m_new > m + 8.0f;
+#if !CSA_DEFER_ODONE
+          mbar_wait(bar_o, (od + j - 1) & 1, 0x310 + s, p.dbg);
+          tc_fence_after();
+          pv_pending = false;
+#endif
+          if (__any_sync(0xffffffffu, need)) {
+#if CSA_DEFER_ODONE
+            mbar_wait(bar_o, (od + j - 1) & 1, 0x310 + s, p.dbg);
+            tc_fence_after();
+            pv_pending = false;
+#endif
+            const float alpha = need ? fast_exp2(m - m_new) : 1.0f;
+            if (need) m = m_new;
+            l *= alpha;
+            uint32_t ov[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              tmem_ld32(tO + c * 32, ov);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st32(tO + c * 32, ov);
+            }
+          }
+        }
+
+        TRACE(5);
+        const bool more = j + 1 < w.total;
+#if CSA_EARLY_LD == 1
+        // S(j+1) was issued when S(j) was released
+        if (more) {
+          mbar_wait(bar_s, sph, 0x301 + s, p.dbg);
+          sph ^= 1;
+          tc_fence_after();
+        }
+#endif
+
+        // P = exp2(S*scale - m) in chunks of 32 keys: FFMA2 -> MUFU.EX2 -> FADD2 row sum -> pack -> TMEM
+        uint64_t nm2 = pack_f2(-m, -m);
+        uint64_t ls[2] = {0ull, 0ull};
+#if CSA_PINGPONG
+        if (have_token) {
+          have_token = false;
+        } else {
+          named_bar_sync(tok_in, 64);  // the other Q tile's warp on this sub-partition has issued its exponentials
+        }
+        asm volatile("" : "+l"(nm2));  // every exponential depends on nm2: none may be hoisted above the token
+#endif
+        TRACE(6);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint64_t xs[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            xs[i] = ffma2(pack_f2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
+#if CSA_EARLY_LD == 1
+          // the chunk's scores are consumed: refill its registers with the next tile's scores while the MUFU works
+          if (more) tmem_ld32(tS + c * 32, sv[c]);
+#endif
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0, p1;
+            if (poly_pair(i)) {
+              poly_exp2_x2(xs[i], p0, p1);
+            } else {
+              float x0, x1;
+              unpack_f2(xs[i], x0, x1);
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
+            ls[i & 1] = fadd2(ls[i & 1], pack_f2(p0, p1));
+            pk[i] = pack2<kBF16>(p0, p1);
+          }
+          if (c == 0 && pv_pending) {
+            mbar_wait(bar_o, (od + j - 1) & 1, 0x311 + s, p.dbg);
+            tc_fence_after();
+          }
+          tmem_st16(tP + c * 16, pk);
+#if CSA_PINGPONG
+          if (c == CSA_TOKEN_CHUNK) named_bar_arrive(tok_out, 64);  // the other Q tile may start its exponentials
+#endif
+        }
+#if CSA_EARLY_LD == 2
+        // all exponentials are issued: pull the next tile's scores (computed since S(j) was released, an exp phase
+        // ago) so that the TMEM read latency overlaps the P store drain and the p_ready hand-over
+        if (more) {
+          mbar_wait(bar_s, sph, 0x301 + s, p.dbg);
+          sph ^= 1;
+          tc_fence_after();
+          tmem_ld32(tS + 0, sv[0]);
+          tmem_ld32(tS + 32, sv[1]);
+          tmem_ld32(tS + 64, sv[2]);
+          tmem_ld32(tS + 96, sv[3]);
+        }
+#endif
+        TRACE(7);
+        {
+          float a0, a1, b0, b1;
+          unpack_f2(ls[0], a0, a1);
+          unpack_f2(ls[1], b0, b1);
+          l += (a0 + a1) + (b0 + b1);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p);
+        TRACE(8);
+#if CSA_EARLY_LD
+        if (more) {
+          // the next score row now lives in registers: let the tensor core overwrite S
+          tc_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_f);
+        }
+#endif
       }
 
 #endif
       // epilogue: wait for the last PV, normalise, store
+      TRACE(11);
       mbar_wait(bar_o, (od + w.total - 1) & 1, 0x320 + s, p.dbg);
       tc_fence_after();
+      TRACE(12);
       od += w.total;
       const float inv = 1.0f / l;
 #pragma unroll
@@ -893,7 +1074,7 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       }
       tc_fence_before();
     }
-#if CSA_PINGPONG && !CSA_SOFTMAX_PIPE
+#if CSA_PINGPONG
     // Q tile 1's last hand-over has no taker: absorb it so that no barrier is left half-arrived at exit
     if (s == 0 && !have_token) named_bar_sync(tok_in, 64);
 #endif
@@ -1027,4 +1208,16 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
   ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_error(static_cast<int>(ce), "csa_attn_kernel launch: %s", cudaGetErrorString(ce));
   return 0;
+}
+
+// Debug builds only (-DCSA_TRACE=1): device buffer of kTraceSlots * kTraceEvents 64-bit words for the timeline trace.
+extern "C" int csa_debug_set_trace(void* dev_buffer) {
+#if CSA_TRACE
+  cudaError_t ce = cudaMemcpyToSymbol(csa::g_trace, &dev_buffer, sizeof(dev_buffer));
+  if (ce != cudaSuccess) return set_error(static_cast<int>(ce), "csa_debug_set_trace: %s", cudaGetErrorString(ce));
+  return 0;
+#else
+  (void)dev_buffer;
+  return set_error(CSA_E_BADARG, "csa_debug_set_trace: library built without CSA_TRACE");
+#endif
 }

@@ -49,34 +49,39 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 
 // Watchdog: a kernel that would otherwise spin forever on a barrier (a protocol bug) records where it was
 // stuck and traps, so a bad build costs one failed launch instead of a hung GPU box.
-#ifndef CSA_WATCHDOG_NS
-#define CSA_WATCHDOG_NS 4000000000ull
-#endif
 // `dbg` points at 4 words of host-mapped pinned memory {tag, blockIdx.x, threadIdx.x, parity} (or is null), so
-// the record survives the trap that kills the context.
+// the record survives the trap that kills the context.  The limit is a poll count (each try_wait suspends the
+// thread for a hardware time slice, so 2^26 polls is many seconds): no timer reads, a handful of instructions.
+#ifndef CSA_WATCHDOG_POLLS
+#define CSA_WATCHDOG_POLLS (1u << 26)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0,
                                           volatile uint32_t* dbg = nullptr) {
   if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
-  uint64_t t0 = 0;
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins == 4096u) {
-      spins = 0;
-      const uint64_t now = globaltimer_ns();
-      if (t0 == 0) {
-        t0 = now;
-      } else if (now - t0 > CSA_WATCHDOG_NS) {
-        if (dbg != nullptr && dbg[0] == 0u) {
-          dbg[1] = blockIdx.x;
-          dbg[2] = threadIdx.x;
-          dbg[3] = parity;
-          dbg[0] = tag | 0x80000000u;
-        }
-        __threadfence_system();
-        asm volatile("trap;");
+    if (++polls == CSA_WATCHDOG_POLLS) {
+      if (dbg != nullptr && dbg[0] == 0u) {
+        dbg[1] = blockIdx.x;
+        dbg[2] = threadIdx.x;
+        dbg[3] = parity;
+        dbg[0] = tag | 0x80000000u;
       }
+      __threadfence_system();
+      asm volatile("trap;");
     }
   }
+}
+
+// One lane of a converged warp (the same lane every time: the lowest active one).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ----------------------------------------------------------------------------------------------- TMA

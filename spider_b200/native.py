@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "csa_last_error",
     "csa_device_supported",
     "csa_debug_stuck",
+    "csa_debug_set_trace",
     "csa_compact_rows",
     "csa_validate_mask",
     "csa_gather_rows",
@@ -129,6 +130,8 @@ def load() -> ctypes.CDLL:
     lib.csa_device_supported.argtypes = [c_int32]
     lib.csa_debug_stuck.restype = c_int32
     lib.csa_debug_stuck.argtypes = [POINTER(c_uint32)]
+    lib.csa_debug_set_trace.restype = c_int32
+    lib.csa_debug_set_trace.argtypes = [c_void_p]
     lib.csa_compact_rows.restype = c_int32
     lib.csa_compact_rows.argtypes = [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64,
                                      c_void_p, c_void_p]
