@@ -55,6 +55,11 @@
 #ifndef CSA_DEFER_ODONE
 #define CSA_DEFER_ODONE 0
 #endif
+// Kernel organisation: 0 = 128-key score tiles, S and P single-buffered in TMEM (csa_attn_kernel);
+// 1 = 64-key half tiles with double-buffered S and P and an in-warp software pipeline (csa_attn_kernel_h64).
+#ifndef CSA_H64
+#define CSA_H64 0
+#endif
 
 // Timeline trace (debug builds only, -DCSA_TRACE=1): lane 0 of a few warps of CTA 0 records (event, clock) pairs
 // into a device buffer set with csa_debug_set_trace(); tools/trace_timeline.py turns them into per-tile latencies.
@@ -124,6 +129,8 @@ struct __align__(1024) AttnSmem {
   uint64_t k_full[kKStages], k_empty[kKStages];
   uint64_t v_full[kVStages], v_empty[kVStages];
   uint64_t s_full[2], s_free[2], p_ready[2], o_done[2];
+  // half-tile organisation (csa_attn_kernel_h64): [Q tile][S / P buffer]
+  uint64_t h_s_full[2][2], h_s_free[2][2], h_p_ready[2][2], h_pv_done[2][2];
   uint32_t tmem_base;
   float xch_max[2][2][2][kBM];  // [Q tile][tile parity][column half][row]: partial row maxima (row split only)
   float xch_sum[2][2][kBM];     // [Q tile][column half][row]: partial row sums at the end of a unit
@@ -267,6 +274,100 @@ __device__ __forceinline__ int tile_valid(const Unit& w, int t) {
   return rem < kBN ? rem : kBN;
 }
 
+// 32-bit shared-window address of a field of AttnSmem, given the address `sb` of the (aligned) struct
+#define SB(field) (sb + static_cast<uint32_t>(offsetof(AttnSmem, field)))
+
+// =============================================================================================== producer warp
+// TMA producer shared by both kernel organisations: Q tiles (box 64x128) and 128-key K/V tiles, either as one tiled
+// load (contiguous run of keys) or as 32 lane-parallel `tile::gather4` loads into the same 128B-swizzled stage.
+__device__ __forceinline__ void producer_warp(const AttnKernelParams& p, const uint32_t sb, const int lane) {
+  int ks = 0, vs = 0;
+  uint32_t kph = 0, vph = 0, qph = 0;
+  for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    const Unit w = decode_unit(p, u);
+    if (w.total == 0) continue;
+    const int col = w.h * kHD;
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_wait((SB(q_empty) + 8u * (s)), qph ^ 1, 0x100 + s, p.dbg);
+        mbar_arrive_expect_tx((SB(q_full) + 8u * (s)), kTileBytes);
+        tma_load_2d(&p.tm_q, (SB(q) + static_cast<uint32_t>(kTileBytes) * (s)), (SB(q_full) + 8u * (s)), col, w.q_row0 + s * kBM);
+      }
+    }
+    qph ^= 1;
+    int last_idx = 0;
+    if (w.ng > 0) last_idx = __ldg(w.gidx + w.ng - 1);
+
+    for (int t = 0; t < w.total; ++t) {
+      // decide how tile t is fetched
+      bool gather = false;
+      const CUtensorMap* mk;
+      const CUtensorMap* mv;
+      int row0 = 0;
+      int4 iv = make_int4(0, 0, 0, 0);
+      if (t < w.tg) {
+        const int valid = min(kBN, w.ng - t * kBN);
+        const int pos = t * kBN + lane * 4;
+        iv = __ldg(reinterpret_cast<const int4*>(w.gidx + pos));
+        if (pos + 0 >= w.ng) iv.x = last_idx;
+        if (pos + 1 >= w.ng) iv.y = last_idx;
+        if (pos + 2 >= w.ng) iv.z = last_idx;
+        if (pos + 3 >= w.ng) iv.w = last_idx;
+        // contiguous run?  (lists are strictly ascending, so first/last decide)
+        const int first = __shfl_sync(0xffffffffu, iv.x, 0);
+        const int lpos = valid - 1;
+        const int src_lane = lpos >> 2;
+        const int c0 = __shfl_sync(0xffffffffu, iv.x, src_lane);
+        const int c1 = __shfl_sync(0xffffffffu, iv.y, src_lane);
+        const int c2 = __shfl_sync(0xffffffffu, iv.z, src_lane);
+        const int c3 = __shfl_sync(0xffffffffu, iv.w, src_lane);
+        const int sel = lpos & 3;
+        const int lastv = sel == 0 ? c0 : (sel == 1 ? c1 : (sel == 2 ? c2 : c3));
+        gather = (lastv - first) != lpos;
+        row0 = w.a_base + first;
+        mk = gather ? &p.tm_kag : &p.tm_ka;
+        mv = gather ? &p.tm_vag : &p.tm_va;
+        iv.x += w.a_base;
+        iv.y += w.a_base;
+        iv.z += w.a_base;
+        iv.w += w.a_base;
+      } else {
+        int seg, local;
+        locate_tile(w, t, seg, local);
+        const int srow = seg == 0 ? w.seg_row[0] : (seg == 1 ? w.seg_row[1] : w.seg_row[2]);
+        row0 = srow + local * kBN;
+        const bool in_b = seg >= w.seg_b;
+        mk = in_b ? &p.tm_kb : &p.tm_ka;
+        mv = in_b ? &p.tm_vb : &p.tm_va;
+      }
+      // ---- K
+      if (lane == 0) {
+        mbar_wait((SB(k_empty) + 8u * (ks)), kph ^ 1, 0x110, p.dbg);
+        mbar_arrive_expect_tx((SB(k_full) + 8u * (ks)), kTileBytes);
+      }
+      __syncwarp();
+      if (gather) {
+        tma_gather4(mk, (SB(k) + static_cast<uint32_t>(kTileBytes) * (ks)) + lane * 512, (SB(k_full) + 8u * (ks)), col, iv.x, iv.y, iv.z, iv.w);
+      } else if (lane == 0) {
+        tma_load_2d(mk, (SB(k) + static_cast<uint32_t>(kTileBytes) * (ks)), (SB(k_full) + 8u * (ks)), col, row0);
+      }
+      if (++ks == kKStages) { ks = 0; kph ^= 1; }
+      // ---- V
+      if (lane == 0) {
+        mbar_wait((SB(v_empty) + 8u * (vs)), vph ^ 1, 0x120, p.dbg);
+        mbar_arrive_expect_tx((SB(v_full) + 8u * (vs)), kTileBytes);
+      }
+      __syncwarp();
+      if (gather) {
+        tma_gather4(mv, (SB(v) + static_cast<uint32_t>(kTileBytes) * (vs)) + lane * 512, (SB(v_full) + 8u * (vs)), col, iv.x, iv.y, iv.z, iv.w);
+      } else if (lane == 0) {
+        tma_load_2d(mv, (SB(v) + static_cast<uint32_t>(kTileBytes) * (vs)), (SB(v_full) + 8u * (vs)), col, row0);
+      }
+      if (++vs == kVStages) { vs = 0; vph ^= 1; }
+    }
+  }
+}
+
 template <bool kBF16>
 __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_constant__ AttnKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -277,8 +378,6 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
   // 32-bit shared-window address of the (aligned) storage; every barrier / tile address below is sb + constant, so
   // no generic->shared conversion is redone inside the loops
   const uint32_t sb = smem_u32(&sm);
-#define SB(field) (sb + static_cast<uint32_t>(offsetof(AttnSmem, field)))
-
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_q);
     tma_prefetch_desc(&p.tm_ka);
@@ -319,92 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
   // (setmaxnreg sits at the top of each role branch so that ptxas budgets every branch separately)
   if (warp == 0) {
     setmaxnreg_dec<kRegsCtl>();
-    // =========================================================================================== producer
-    int ks = 0, vs = 0;
-    uint32_t kph = 0, vph = 0, qph = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const Unit w = decode_unit(p, u);
-      if (w.total == 0) continue;
-      const int col = w.h * kHD;
-      if (lane == 0) {
-        for (int s = 0; s < 2; ++s) {
-          mbar_wait((SB(q_empty) + 8u * (s)), qph ^ 1, 0x100 + s, p.dbg);
-          mbar_arrive_expect_tx((SB(q_full) + 8u * (s)), kTileBytes);
-          tma_load_2d(&p.tm_q, (SB(q) + static_cast<uint32_t>(kTileBytes) * (s)), (SB(q_full) + 8u * (s)), col, w.q_row0 + s * kBM);
-        }
-      }
-      qph ^= 1;
-      int last_idx = 0;
-      if (w.ng > 0) last_idx = __ldg(w.gidx + w.ng - 1);
-
-      for (int t = 0; t < w.total; ++t) {
-        // decide how tile t is fetched
-        bool gather = false;
-        const CUtensorMap* mk;
-        const CUtensorMap* mv;
-        int row0 = 0;
-        int4 iv = make_int4(0, 0, 0, 0);
-        if (t < w.tg) {
-          const int valid = min(kBN, w.ng - t * kBN);
-          const int pos = t * kBN + lane * 4;
-          iv = __ldg(reinterpret_cast<const int4*>(w.gidx + pos));
-          if (pos + 0 >= w.ng) iv.x = last_idx;
-          if (pos + 1 >= w.ng) iv.y = last_idx;
-          if (pos + 2 >= w.ng) iv.z = last_idx;
-          if (pos + 3 >= w.ng) iv.w = last_idx;
-          // contiguous run?  (lists are strictly ascending, so first/last decide)
-          const int first = __shfl_sync(0xffffffffu, iv.x, 0);
-          const int lpos = valid - 1;
-          const int src_lane = lpos >> 2;
-          const int c0 = __shfl_sync(0xffffffffu, iv.x, src_lane);
-          const int c1 = __shfl_sync(0xffffffffu, iv.y, src_lane);
-          const int c2 = __shfl_sync(0xffffffffu, iv.z, src_lane);
-          const int c3 = __shfl_sync(0xffffffffu, iv.w, src_lane);
-          const int sel = lpos & 3;
-          const int lastv = sel == 0 ? c0 : (sel == 1 ? c1 : (sel == 2 ? c2 : c3));
-          gather = (lastv - first) != lpos;
-          row0 = w.a_base + first;
-          mk = gather ? &p.tm_kag : &p.tm_ka;
-          mv = gather ? &p.tm_vag : &p.tm_va;
-          iv.x += w.a_base;
-          iv.y += w.a_base;
-          iv.z += w.a_base;
-          iv.w += w.a_base;
-        } else {
-          int seg, local;
-          locate_tile(w, t, seg, local);
-          const int srow = seg == 0 ? w.seg_row[0] : (seg == 1 ? w.seg_row[1] : w.seg_row[2]);
-          row0 = srow + local * kBN;
-          const bool in_b = seg >= w.seg_b;
-          mk = in_b ? &p.tm_kb : &p.tm_ka;
-          mv = in_b ? &p.tm_vb : &p.tm_va;
-        }
-        // ---- K
-        if (lane == 0) {
-          mbar_wait((SB(k_empty) + 8u * (ks)), kph ^ 1, 0x110, p.dbg);
-          mbar_arrive_expect_tx((SB(k_full) + 8u * (ks)), kTileBytes);
-        }
-        __syncwarp();
-        if (gather) {
-          tma_gather4(mk, (SB(k) + static_cast<uint32_t>(kTileBytes) * (ks)) + lane * 512, (SB(k_full) + 8u * (ks)), col, iv.x, iv.y, iv.z, iv.w);
-        } else if (lane == 0) {
-          tma_load_2d(mk, (SB(k) + static_cast<uint32_t>(kTileBytes) * (ks)), (SB(k_full) + 8u * (ks)), col, row0);
-        }
-        if (++ks == kKStages) { ks = 0; kph ^= 1; }
-        // ---- V
-        if (lane == 0) {
-          mbar_wait((SB(v_empty) + 8u * (vs)), vph ^ 1, 0x120, p.dbg);
-          mbar_arrive_expect_tx((SB(v_full) + 8u * (vs)), kTileBytes);
-        }
-        __syncwarp();
-        if (gather) {
-          tma_gather4(mv, (SB(v) + static_cast<uint32_t>(kTileBytes) * (vs)) + lane * 512, (SB(v_full) + 8u * (vs)), col, iv.x, iv.y, iv.z, iv.w);
-        } else if (lane == 0) {
-          tma_load_2d(mv, (SB(v) + static_cast<uint32_t>(kTileBytes) * (vs)), (SB(v_full) + 8u * (vs)), col, row0);
-        }
-        if (++vs == kVStages) { vs = 0; vph ^= 1; }
-      }
-    }
+    producer_warp(p, sb, lane);
   } else if (warp == 1 || warp == 3) {
     // =========================================================================================== MMA issue
     // One issuing thread per Q tile (warp 1: tile 0, warp 3: tile 1).  The two instruction streams are independent,
@@ -1088,6 +1102,430 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
   }
 }
 
+
+// =================================================================================================================
+// Half-tile organisation.  TMEM holds, per Q tile, two 64-key score buffers, two P buffers and O:
+//   Q tile s at column 256*s:  S[0] +0, S[1] +64 | P[0] +128, P[1] +160 (64 16-bit values = 32 columns) | O +192.
+// Double buffering removes both couplings of the 128-key organisation (S(j+1) cannot be produced before S(j) is
+// read; P(j+1) cannot be written before PV(j) has drained), which is what allows a softmax thread to read and
+// reduce the next half tile's scores *inside* the MUFU-bound exponential block of the current one.
+// Half tile g (a per-Q-tile counter that runs across units) uses buffer g & 1; every barrier below completes once
+// per use of its buffer, so the parity a role waits for is a function of g alone.
+constexpr int kHN = 64;  // keys per half tile
+
+// Walks the 64-key half tiles of a unit in order.  Segments (gathered list, A run 1, A run 2, B run) are padded to
+// whole 128-key smem tiles by the producer, so a segment of L keys has ceil(L/64) half tiles and half tile i of a
+// segment lives in rows [64 * (i & 1), +64) of smem tile i / 2 of that segment.
+struct HalfWalker {
+  int l1, l2, l3;  // lengths of the segments after the current one
+  int rem;         // keys left in the current segment
+  int h;           // which half of its smem tile the next half tile is
+  __device__ __forceinline__ void skip_empty() {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (rem <= 0) {
+        rem = l1;
+        l1 = l2;
+        l2 = l3;
+        l3 = 0;
+      }
+    }
+  }
+  __device__ __forceinline__ void init(const Unit& w) {
+    rem = w.ng;
+    l1 = w.seg_len[0];
+    l2 = w.seg_len[1];
+    l3 = w.seg_len[2];
+    h = 0;
+    skip_empty();
+  }
+  // valid keys of the next half tile; `half` = its half of the smem tile, `last` = it is the last one of that tile
+  __device__ __forceinline__ int next(int& half, bool& last) {
+    const int v = rem < kHN ? rem : kHN;
+    half = h;
+    rem -= kHN;
+    last = (h == 1) || (rem <= 0);
+    h = last ? 0 : 1;
+    skip_empty();
+    return v;
+  }
+  __device__ __forceinline__ int next() {
+    int half;
+    bool last;
+    return next(half, last);
+  }
+};
+
+__device__ __forceinline__ int unit_halves(const Unit& w) {
+  int n = (w.ng + kHN - 1) / kHN;
+#pragma unroll
+  for (int i = 0; i < kMaxSeg; ++i) n += (w.seg_len[i] + kHN - 1) / kHN;
+  return n;
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel_h64(const __grid_constant__ AttnKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  AttnSmem& sm = *reinterpret_cast<AttnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t sb = smem_u32(&sm);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_q);
+    tma_prefetch_desc(&p.tm_ka);
+    tma_prefetch_desc(&p.tm_va);
+    tma_prefetch_desc(&p.tm_kag);
+    tma_prefetch_desc(&p.tm_vag);
+    tma_prefetch_desc(&p.tm_kb);
+    tma_prefetch_desc(&p.tm_vb);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init((SB(q_full) + 8u * (i)), 1);
+      mbar_init((SB(q_empty) + 8u * (i)), 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init((SB(h_s_full) + 8u * (2 * i + b)), 1);
+        mbar_init((SB(h_s_free) + 8u * (2 * i + b)), 4);   // one arrival per softmax warp of the Q tile
+        mbar_init((SB(h_p_ready) + 8u * (2 * i + b)), 4);
+        mbar_init((SB(h_pv_done) + 8u * (2 * i + b)), 1);
+      }
+    }
+    for (int i = 0; i < kKStages; ++i) {
+      mbar_init((SB(k_full) + 8u * (i)), 1);
+      mbar_init((SB(k_empty) + 8u * (i)), 2);  // one commit per MMA stream
+    }
+    for (int i = 0; i < kVStages; ++i) {
+      mbar_init((SB(v_full) + 8u * (i)), 1);
+      mbar_init((SB(v_empty) + 8u * (i)), 2);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<512>(SB(tmem_base));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    setmaxnreg_dec<kRegsCtl>();
+    producer_warp(p, sb, lane);
+  } else if (warp == 1 || warp == 3) {
+    // =========================================================================================== MMA issue
+    // One warp per Q tile, warp-uniform control flow, one elected lane issues.  Per unit: QK(0), QK(1), then
+    // { QK(i+2), PV(i) }: the scores run two half tiles ahead, so S(i+1) is in TMEM a whole exponential block
+    // before the softmax threads want it.
+    setmaxnreg_dec<kRegsCtl>();
+    const int s = __shfl_sync(0xffffffffu, warp >> 1, 0);
+    constexpr uint32_t idesc_qk = make_idesc(kBM, kHN, kBF16 ? 1 : 0, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc(kBM, kHD, kBF16 ? 1 : 0, 0, 1);
+    const uint32_t tbase = tmem + s * 256;
+    const uint32_t bar_qf = (SB(q_full) + 8u * (s)), bar_qe = (SB(q_empty) + 8u * (s));
+    const uint32_t bar_sfull = SB(h_s_full) + 16u * s, bar_sfree = SB(h_s_free) + 16u * s;
+    const uint32_t bar_pready = SB(h_p_ready) + 16u * s, bar_pvdone = SB(h_pv_done) + 16u * s;
+    const uint64_t dq = make_sw128_desc((SB(q) + static_cast<uint32_t>(kTileBytes) * (s)));
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0, qph = 0;
+    uint32_t gq = 0, gp = 0;  // half tiles whose QK / PV has been issued, over the whole kernel
+    TRACE_INIT(2 + s, lane == 0);
+
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const Unit w = decode_unit(p, u);
+      if (w.total == 0) continue;
+      const int n = unit_halves(w);
+      HalfWalker wq, wp;
+      wq.init(w);
+      wp.init(w);
+      int iq = 0;  // half tiles of this unit whose QK has been issued
+
+      auto qk_step = [&]() {
+        int half;
+        bool last;
+        wq.next(half, last);
+        const uint32_t b = gq & 1u;
+        TRACE(20);
+        if (half == 0) mbar_wait((SB(k_full) + 8u * (ks)), kph, 0x201 + s, p.dbg);
+        mbar_wait(bar_sfree + 8u * b, ((gq >> 1) & 1u) ^ 1u, 0x203 + s, p.dbg);  // S[b] has been read (half tile gq-2)
+        tc_fence_after();
+        TRACE(22);
+        const uint64_t dk =
+            make_sw128_desc((SB(k) + static_cast<uint32_t>(kTileBytes) * (ks)) + static_cast<uint32_t>(half) * (kHN * 128));
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < kHD / 16; ++kk) mma_ss(tbase + b * kHN, dq + kk * 2, dk + kk * 2, idesc_qk, kk > 0 ? 1u : 0u);
+          tc_commit(bar_sfull + 8u * b);
+          if (last) tc_commit((SB(k_empty) + 8u * (ks)));
+          if (iq == n - 1) tc_commit(bar_qe);
+        }
+        __syncwarp();
+        if (last) {
+          if (++ks == kKStages) { ks = 0; kph ^= 1; }
+        }
+        ++gq;
+        ++iq;
+      };
+
+      mbar_wait(bar_qf, qph, 0x200 + s, p.dbg);
+      qph ^= 1;
+      qk_step();
+      if (n > 1) qk_step();
+      for (int i = 0; i < n; ++i) {
+        if (i + 2 < n) qk_step();
+        int half;
+        bool last;
+        wp.next(half, last);
+        const uint32_t b = gp & 1u;
+        TRACE(23);
+        if (half == 0) mbar_wait((SB(v_full) + 8u * (vs)), vph, 0x210 + s, p.dbg);
+        mbar_wait(bar_pready + 8u * b, (gp >> 1) & 1u, 0x212 + s, p.dbg);
+        tc_fence_after();
+        TRACE(25);
+        const uint64_t dv =
+            make_sw128_desc((SB(v) + static_cast<uint32_t>(kTileBytes) * (vs)) + static_cast<uint32_t>(half) * (kHN * 128));
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < kHN / 16; ++kk) {
+            // 16 keys = 16 rows of 128 B along the contraction dim (MN-major B); 16 16-bit P values = 8 columns
+            mma_ts(tbase + 192, tbase + 128 + b * 32 + kk * 8, dv + kk * (2048 >> 4), idesc_pv,
+                   (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          tc_commit(bar_pvdone + 8u * b);
+          if (last) tc_commit((SB(v_empty) + 8u * (vs)));
+        }
+        __syncwarp();
+        TRACE(26);
+        if (last) {
+          if (++vs == kVStages) { vs = 0; vph ^= 1; }
+        }
+        ++gp;
+      }
+    }
+  } else if (warp == 2) {
+    setmaxnreg_dec<kRegsCtl>();
+  } else {
+    // =========================================================================================== softmax
+    // Thread == query row.  Steady state of one step (half tile g in `cur`, already masked, its row max folded
+    // into m): pull S(g+1) into `nxt` (tcgen05.ld, asynchronous), exponentiate the first 32 keys of `cur`, then
+    // in ONE basic block exponentiate the other 32 keys and reduce the row max of `nxt` — the FMNMX3 chain fills
+    // issue slots the MUFU-paced exponentials leave empty.  P(g) goes to its own TMEM buffer, so nothing here waits
+    // for the PV of the previous half tile, and S(g+1) was produced during the previous step.
+    setmaxnreg_inc<kRegsSoftmax>();
+    const int s = (warp - 4) >> 2;
+    const int row = ((warp & 3) << 5) | lane;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) << 5) << 16;
+    const uint32_t tbase = tmem + lane_base + s * 256;
+    const uint32_t bar_sfull = SB(h_s_full) + 16u * s, bar_sfree = SB(h_s_free) + 16u * s;
+    const uint32_t bar_pready = SB(h_p_ready) + 16u * s, bar_pvdone = SB(h_pv_done) + 16u * s;
+    const float sc = p.scale_log2;
+    const uint64_t sc2 = pack_f2(sc, sc);
+    uint32_t g0 = 0;  // half tiles of earlier units
+#if CSA_PINGPONG
+    const int tok_in = 1 + 2 * (warp & 3) + (s ^ 1);
+    const int tok_out = 1 + 2 * (warp & 3) + s;
+    bool have_token = (s == 0);
+#endif
+    TRACE_INIT(s, (warp & 3) == 0 && lane == 0);
+
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const Unit w = decode_unit(p, u);
+      const int q_in_frame = w.qp * (2 * kBM) + s * kBM + row;
+      const bool row_ok = q_in_frame < p.n_q;
+      uint4* optr = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
+                                             static_cast<int64_t>(w.q_row0 + s * kBM + row) * p.o_ld + w.h * kHD);
+      if (w.total == 0) {
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) optr[i] = make_uint4(0, 0, 0, 0);
+        }
+        continue;
+      }
+      const int n = unit_halves(w);
+      HalfWalker walk;
+      walk.init(w);
+      float m, l = 0.f;
+      uint32_t sva[2][32], svb[2][32];  // two half tiles of scores: the one being exponentiated and the next one
+
+      auto mask_tail = [&](uint32_t (&x)[2][32], const int valid) {
+        if (valid < kHN) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) x[c][i] = 0xff800000u;  // -inf
+        }
+      };
+      auto row_max = [&](const uint32_t (&x)[2][32]) {
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2)
+            mx[(i >> 1) & 3] = fmax3(mx[(i >> 1) & 3], __uint_as_float(x[c][i]), __uint_as_float(x[c][i + 1]));
+        return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      };
+
+      // prologue: the unit's first half tile
+      {
+        const uint32_t b = g0 & 1u;
+        mbar_wait(bar_sfull + 8u * b, (g0 >> 1) & 1u, 0x300 + s, p.dbg);
+        tc_fence_after();
+        tmem_ld32(tbase + b * kHN + 0, sva[0]);
+        tmem_ld32(tbase + b * kHN + 32, sva[1]);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sfree + 8u * b);
+        mask_tail(sva, walk.next());
+        m = row_max(sva) * sc;
+      }
+
+      // one step: exponentiate `cur` (half tile i of the unit), prefetch and reduce `nxt`
+      auto step = [&](uint32_t (&cur)[2][32], uint32_t (&nxt)[2][32], const int i) {
+        const uint32_t g = g0 + static_cast<uint32_t>(i);
+        const uint32_t b = g & 1u, bn = b ^ 1u;
+        const bool more = i + 1 < n;
+        TRACE(1);
+        if (more) mbar_wait(bar_sfull + 8u * bn, ((g + 1) >> 1) & 1u, 0x301 + s, p.dbg);  // S(g+1) is computed
+        mbar_wait(bar_pvdone + 8u * b, ((g >> 1) & 1u) ^ 1u, 0x310 + s, p.dbg);            // PV(g-2) has drained P[b]
+        tc_fence_after();
+        TRACE(2);
+        if (more) {
+          tmem_ld32(tbase + bn * kHN + 0, nxt[0]);
+          tmem_ld32(tbase + bn * kHN + 32, nxt[1]);
+        }
+        uint64_t nm2 = pack_f2(-m, -m);
+        uint64_t ls[2] = {0ull, 0ull};
+#if CSA_PINGPONG
+        if (have_token) {
+          have_token = false;
+        } else {
+          named_bar_sync(tok_in, 64);
+        }
+        asm volatile("" : "+l"(nm2));
+#endif
+        TRACE(6);
+        float mxn = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint64_t xs[16];
+#pragma unroll
+          for (int k2 = 0; k2 < 16; ++k2)
+            xs[k2] = ffma2(pack_f2(__uint_as_float(cur[c][2 * k2]), __uint_as_float(cur[c][2 * k2 + 1])), sc2, nm2);
+          if (c == 1 && more) {
+            // the next half tile's scores have landed (they were requested 32 exponentials ago)
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sfree + 8u * bn);
+            mask_tail(nxt, walk.next());
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int k2 = 0; k2 < 16; ++k2) {
+            float p0, p1;
+            if (poly_pair(k2)) {
+              poly_exp2_x2(xs[k2], p0, p1);
+            } else {
+              float x0, x1;
+              unpack_f2(xs[k2], x0, x1);
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
+            ls[k2 & 1] = fadd2(ls[k2 & 1], pack_f2(p0, p1));
+            pk[k2] = pack2<kBF16>(p0, p1);
+          }
+          if (c == 1 && more) mxn = row_max(nxt);  // same basic block as the exponentials above
+          tmem_st16(tbase + 128 + b * 32 + c * 16, pk);
+#if CSA_PINGPONG
+          if (c == (CSA_TOKEN_CHUNK >= 2 ? 1 : 0)) named_bar_arrive(tok_out, 64);
+#endif
+        }
+        TRACE(7);
+        {
+          float a0, a1, b0, b1;
+          unpack_f2(ls[0], a0, a1);
+          unpack_f2(ls[1], b0, b1);
+          l += (a0 + a1) + (b0 + b1);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pready + 8u * b);
+        TRACE(8);
+        if (more) {
+          // lazy rescale: only when the running max grows by more than 2^8 does O (and l) get rescaled — after the
+          // PV of this half tile has completed and before the next one can be issued (its p_ready comes later)
+          const float m_new = fmaxf(m, mxn * sc);
+          const bool need = m_new > m + 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(bar_pvdone + 8u * b, (g >> 1) & 1u, 0x311 + s, p.dbg);
+            tc_fence_after();
+            const float alpha = need ? fast_exp2(m - m_new) : 1.0f;
+            if (need) m = m_new;
+            l *= alpha;
+            uint32_t ov[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              tmem_ld32(tbase + 192 + c * 32, ov);
+              tc_wait_ld();
+#pragma unroll
+              for (int k2 = 0; k2 < 32; ++k2) ov[k2] = __float_as_uint(__uint_as_float(ov[k2]) * alpha);
+              tmem_st32(tbase + 192 + c * 32, ov);
+            }
+            tc_wait_st();
+            tc_fence_before();
+          }
+        }
+      };
+
+      for (int i = 0; i < n; i += 2) {
+        step(sva, svb, i);
+        if (i + 1 < n) step(svb, sva, i + 1);
+      }
+
+      // epilogue: wait for the last PV, normalise, store
+      {
+        const uint32_t gl = g0 + static_cast<uint32_t>(n) - 1u;
+        TRACE(11);
+        mbar_wait(bar_pvdone + 8u * (gl & 1u), (gl >> 1) & 1u, 0x320 + s, p.dbg);
+        tc_fence_after();
+        TRACE(12);
+      }
+      g0 += static_cast<uint32_t>(n);
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tmem_ld32(tbase + 192 + c * 32, ov);
+        tc_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 v4;
+            v4.x = pack2<kBF16>(__uint_as_float(ov[8 * i + 0]) * inv, __uint_as_float(ov[8 * i + 1]) * inv);
+            v4.y = pack2<kBF16>(__uint_as_float(ov[8 * i + 2]) * inv, __uint_as_float(ov[8 * i + 3]) * inv);
+            v4.z = pack2<kBF16>(__uint_as_float(ov[8 * i + 4]) * inv, __uint_as_float(ov[8 * i + 5]) * inv);
+            v4.w = pack2<kBF16>(__uint_as_float(ov[8 * i + 6]) * inv, __uint_as_float(ov[8 * i + 7]) * inv);
+            optr[c * 4 + i] = v4;
+          }
+        }
+      }
+      tc_fence_before();
+    }
+#if CSA_PINGPONG
+    if (s == 0 && !have_token) named_bar_sync(tok_in, 64);
+#endif
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- host side
 static int encode_2d(CUtensorMap* tm, int dtype, const void* base, int64_t rows, int64_t cols, int64_t ld_elems,
                      uint32_t box_rows) {
@@ -1200,7 +1638,11 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
   if (a->max_ctas > 0 && grid > a->max_ctas) grid = a->max_ctas;
 
   const size_t smem = sizeof(AttnSmem) + 1024;
+#if CSA_H64 && CSA_ROW_SPLIT == 1
+  auto kern = a->dtype == CSA_DTYPE_BF16 ? csa_attn_kernel_h64<true> : csa_attn_kernel_h64<false>;
+#else
   auto kern = a->dtype == CSA_DTYPE_BF16 ? csa_attn_kernel<true> : csa_attn_kernel<false>;
+#endif
   ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (ce != cudaSuccess)
     return set_error(static_cast<int>(ce), "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(ce));
