@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CSA_ABI_VERSION 2
+#define CSA_ABI_VERSION 3
 
 #define CSA_E_BADARG (-1)   /* null pointer, non-positive size, misaligned pointer/stride */
 #define CSA_E_SHAPE (-2)    /* unsupported geometry (head_dim != 64, row stride not 16-byte aligned, ...) */
@@ -187,9 +187,31 @@ typedef struct csa_attn_args {
   const int32_t* ranges; /* optional device int32[...][4], replaces ca_* (see above); 16-byte aligned */
   int32_t range_base;
   int32_t range_step;
+
+  /* Optional scratch for the tail split (see below): device memory, 16-byte aligned, at least
+   * csa_attn_workspace_bytes(max_ctas) bytes, ZERO when first handed to the library (the kernel leaves its header
+   * zero again); one workspace must not be shared by launches that may run concurrently.  NULL = never split. */
+  void* workspace;
+  int64_t workspace_bytes;
 } csa_attn_args_t;
 
+#define CSA_ATTN_NO_SPLIT 1 /* flags: process every unit whole even if a workspace is given */
+
+/*
+ * Work decomposition.  A unit = (group, frame, head, pair of 128-query tiles); units are dealt round-robin to one
+ * persistent CTA per SM.  When the unit count is not a multiple of the CTA count, the units of the last, partial
+ * round are cut into k <= 8 pieces along their keys so that every SM stays busy; pieces leave unnormalised partial
+ * results (O, row max, row sum) in the workspace and the CTA that delivers the last piece of a unit merges them.
+ * Results are independent of the split up to fp32 rounding of the merge.
+ */
 int csa_attn_fwd(const csa_attn_args_t* args, void* stream);
+
+/* Work decomposition of this thread's last csa_attn_fwd: out[4] = {CTAs, whole units, pieces per split unit,
+ * scheduled work items}.  Debug / test aid. */
+int csa_debug_last_launch(int32_t* out4_host);
+
+/* Bytes of workspace that let csa_attn_fwd split on `ctas` CTAs (0 = one per SM of the current device). */
+int64_t csa_attn_workspace_bytes(int32_t ctas);
 
 #ifdef __cplusplus
 }

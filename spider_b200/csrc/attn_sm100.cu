@@ -19,17 +19,8 @@
 #include "ptx.cuh"
 #include "csa_internal.h"
 
-// Softmax organisation: 1 = software-pipelined (S(j+1) pulled in place while tile j is exponentiated),
-// 0 = one tile at a time.
-#ifndef CSA_SOFTMAX_PIPE
-#define CSA_SOFTMAX_PIPE 0
-#endif
-// How many of every 16 element pairs take the polynomial exp2 (FMA/ALU pipes) instead of MUFU.EX2.
-// Threads per query row in the softmax: 1 (a thread owns a 128-column score row) or 2 (64 columns each, row max and
-// row sum exchanged through shared memory) — more warps per SM sub-partition to hide the ALU/MUFU latencies.
-#ifndef CSA_ROW_SPLIT
-#define CSA_ROW_SPLIT 1
-#endif
+// How many of every 16 element pairs take the polynomial exp2 (FMA/ALU pipes) instead of MUFU.EX2 (measured
+// neutral: the softmax is bound by the latency chain of a tile iteration, not by MUFU throughput alone).
 #ifndef CSA_POLY_PAIRS
 #define CSA_POLY_PAIRS 0
 #endif
@@ -43,23 +34,12 @@
 // The token is handed over after this 32-key chunk (0..3) of the exp phase has been issued: 3 = strict alternation,
 // smaller = the two exp phases overlap at the seam, which keeps the MUFU queue full across the hand-over.
 #ifndef CSA_TOKEN_CHUNK
-#define CSA_TOKEN_CHUNK 3
+#define CSA_TOKEN_CHUNK 2
 #endif
-// Early score load.  0: a tile's scores are read (tcgen05.ld) at the top of its iteration.  1: the registers of a
-// 32-key chunk are refilled with the next tile's scores as soon as the chunk's FFMA2s have consumed them (measured
-// slower: S(j+1) is then needed an exp phase earlier than the QK that produces it can deliver).  2: the next tile's
-// scores are read right after the last exponential is issued, under the P store drain and the p_ready hand-over.
-#ifndef CSA_EARLY_LD
-#define CSA_EARLY_LD 0
-#endif
-#ifndef CSA_DEFER_ODONE
-#define CSA_DEFER_ODONE 0
-#endif
-// Kernel organisation: 0 = 128-key score tiles, S and P single-buffered in TMEM (csa_attn_kernel);
-// 1 = 64-key half tiles with double-buffered S and P and an in-warp software pipeline (csa_attn_kernel_h64).
-#ifndef CSA_H64
-#define CSA_H64 0
-#endif
+// Organisations that were built, measured slower on B200 and removed ("what did not work"):
+// two threads per score row (row max exchanged through shared memory), software-pipelined score loads inside the exp
+// phase (needs S double-buffered, TMEM is full), deferred PV wait inside the exp phase (a token holder that stalls
+// blocks both Q tiles), 64-key half tiles with double-buffered S/P (per-step barrier latencies dominate).
 
 // Timeline trace (debug builds only, -DCSA_TRACE=1): lane 0 of a few warps of CTA 0 records (event, clock) pairs
 // into a device buffer set with csa_debug_set_trace(); tools/trace_timeline.py turns them into per-tile latencies.
@@ -99,16 +79,9 @@ constexpr int kHD = 64;   // head dim
 constexpr int kTileBytes = kBN * kHD * 2;
 constexpr int kKStages = 4;
 constexpr int kVStages = 4;
-#if CSA_ROW_SPLIT == 2
-// two threads per query row (64 score columns each): 16 softmax warps = 4 per SM sub-partition
-constexpr int kThreads = 128 + 512;
-constexpr int kRegsCtl = 64;       // launch bound 96/thread: (96-64)*128 == (104-96)*512
-constexpr int kRegsSoftmax = 104;
-#else
 constexpr int kThreads = 384;
-constexpr int kRegsCtl = 88;       // producer / MMA / allocator warps after setmaxnreg.dec
-constexpr int kRegsSoftmax = 208;  // softmax warps after setmaxnreg.inc: (168-88)*128 == (208-168)*256
-#endif
+constexpr int kRegsCtl = 72;       // producer / MMA / allocator warps after setmaxnreg.dec
+constexpr int kRegsSoftmax = 216;  // softmax warps after setmaxnreg.inc: 72*128 + 216*256 == 168*384 (the CTA's pool)
 constexpr int kSoftmaxWarpsPerTile = (kThreads - 128) / 64;  // arrivals on s_free / p_ready per Q tile
 
 // TMEM column map (fp32 columns)
@@ -129,11 +102,8 @@ struct __align__(1024) AttnSmem {
   uint64_t k_full[kKStages], k_empty[kKStages];
   uint64_t v_full[kVStages], v_empty[kVStages];
   uint64_t s_full[2], s_free[2], p_ready[2], o_done[2];
-  // half-tile organisation (csa_attn_kernel_h64): [Q tile][S / P buffer]
-  uint64_t h_s_full[2][2], h_s_free[2][2], h_p_ready[2][2], h_pv_done[2][2];
   uint32_t tmem_base;
-  float xch_max[2][2][2][kBM];  // [Q tile][tile parity][column half][row]: partial row maxima (row split only)
-  float xch_sum[2][2][kBM];     // [Q tile][column half][row]: partial row sums at the end of a unit
+  uint32_t merge_flag;  // split units: this CTA delivered the last piece and merges (written by one thread)
 };
 
 struct AttnKernelParams {
@@ -158,7 +128,17 @@ struct AttnKernelParams {
   int32_t range_base, range_step;
   float scale_log2;
   uint32_t* dbg;  // host-mapped watchdog record (may be null)
+  // Tail split: units [0, n_whole) are processed whole; each of the remaining units (fewer than one per CTA) is cut
+  // into `split` pieces along its key tiles, scheduled as units [n_whole, n_sched); the pieces leave unnormalised
+  // partials in `ws` and the CTA that delivers a unit's last piece merges them.
+  int32_t n_whole, split, n_sched;
+  float* ws;           // split pieces: [piece][256 rows][64] O, then [256] m, then [256] l
+  uint32_t* ws_count;  // one arrival counter per split unit (zero between launches)
 };
+
+constexpr int kPieceFloats = 2 * kBM * (kHD + 2);  // partial of one piece of a Q-tile pair
+constexpr int kMaxSplit = 8;
+constexpr int kWsHeaderBytes = 4096;  // arrival counters (one uint32 per split unit), zero between launches
 
 constexpr int kMaxSeg = 3;  // contiguous runs per unit: up to two runs of source A and one of source B
 
@@ -171,10 +151,23 @@ struct Unit {
   int seg_row[kMaxSeg], seg_len[kMaxSeg], seg_tiles[kMaxSeg];
   int seg_b;   // index of the first segment that lives in source B (segments before it are in A)
   int tg, total;
+  int t0, nt;     // this CTA's share of the unit's key tiles: [t0, t0 + nt) (the whole unit unless split)
+  int piece;      // index of the partial in the workspace, or -1 for a whole unit
+  int split_unit; // index of the unit among the split ones (arrival counter), or -1
 };
 
-__device__ __forceinline__ Unit decode_unit(const AttnKernelParams& p, int u) {
+__device__ __forceinline__ Unit decode_unit(const AttnKernelParams& p, int sched) {
   Unit w;
+  int u = sched, pc = 0;
+  w.piece = -1;
+  w.split_unit = -1;
+  if (sched >= p.n_whole) {
+    const int v = sched - p.n_whole;
+    w.split_unit = v / p.split;
+    pc = v - w.split_unit * p.split;
+    w.piece = v;
+    u = p.n_whole + w.split_unit;
+  }
   w.qp = u % p.n_qpairs;
   int r = u / p.n_qpairs;
   w.h = r % p.heads;
@@ -212,6 +205,12 @@ __device__ __forceinline__ Unit decode_unit(const AttnKernelParams& p, int u) {
   for (int i = 0; i < kMaxSeg; ++i) {
     w.seg_tiles[i] = (w.seg_len[i] + kBN - 1) / kBN;
     w.total += w.seg_tiles[i];
+  }
+  w.t0 = 0;
+  w.nt = w.total;
+  if (w.piece >= 0) {
+    w.t0 = (w.total * pc) / p.split;
+    w.nt = (w.total * (pc + 1)) / p.split - w.t0;
   }
   return w;
 }
@@ -283,9 +282,9 @@ __device__ __forceinline__ int tile_valid(const Unit& w, int t) {
 __device__ __forceinline__ void producer_warp(const AttnKernelParams& p, const uint32_t sb, const int lane) {
   int ks = 0, vs = 0;
   uint32_t kph = 0, vph = 0, qph = 0;
-  for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+  for (int u = blockIdx.x; u < p.n_sched; u += gridDim.x) {
     const Unit w = decode_unit(p, u);
-    if (w.total == 0) continue;
+    if (w.nt == 0) continue;
     const int col = w.h * kHD;
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) {
@@ -298,7 +297,7 @@ __device__ __forceinline__ void producer_warp(const AttnKernelParams& p, const u
     int last_idx = 0;
     if (w.ng > 0) last_idx = __ldg(w.gidx + w.ng - 1);
 
-    for (int t = 0; t < w.total; ++t) {
+    for (int t = w.t0; t < w.t0 + w.nt; ++t) {
       // decide how tile t is fetched
       bool gather = false;
       const CUtensorMap* mk;
@@ -373,11 +372,16 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   AttnSmem& sm = *reinterpret_cast<AttnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  // 32-bit shared-window address of the (aligned) storage; every barrier / tile address below is sb + constant, so
-  // no generic->shared conversion is redone inside the loops
-  const uint32_t sb = smem_u32(&sm);
+  // warp, lane and the 32-bit shared-window address of the (aligned) storage are made opaque to the compiler:
+  // otherwise it re-derives them (S2R SR_TID / SR_CgaCtaId / SR_SWINHI chains, ~25 clk each) in front of every
+  // barrier operation of the latency-bound softmax loop instead of keeping three registers
+  int warp_ = threadIdx.x >> 5;
+  int lane_ = threadIdx.x & 31;
+  uint32_t sb_ = smem_u32(&sm);
+  asm volatile("" : "+r"(warp_), "+r"(lane_), "+r"(sb_));
+  const int warp = warp_;
+  const int lane = lane_;
+  const uint32_t sb = sb_;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tm_q);
     tma_prefetch_desc(&p.tm_ka);
@@ -467,17 +471,15 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         if (++ks == kKStages) { ks = 0; kph ^= 1; }
       };
 
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      for (int u = blockIdx.x; u < p.n_sched; u += gridDim.x) {
         const Unit w = decode_unit(p, u);
-        if (w.total == 0) continue;
+        const int nt = w.nt;
+        if (nt == 0) continue;
         mbar_wait(bar_qf, qph, 0x200 + s, p.dbg);
         qph ^= 1;
-        qk_step(w.total == 1);
-        if (w.total > 1) qk_step(w.total == 2);
-        for (int j = 0; j < w.total; ++j) {
-#if CSA_SOFTMAX_PIPE
-          if (j + 2 < w.total) qk_step(j + 3 == w.total);  // F(j+1) and P(j) arrive together: scores first
-#endif
+        qk_step(nt == 1);
+        if (nt > 1) qk_step(nt == 2);
+        for (int j = 0; j < nt; ++j) {
           TRACE(23);
           mbar_wait((SB(v_full) + 8u * (vs)), vph, 0x210 + s, p.dbg);
           TRACE(24);
@@ -499,194 +501,12 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
           __syncwarp();
           TRACE(26);
           if (++vs == kVStages) { vs = 0; vph ^= 1; }
-#if !CSA_SOFTMAX_PIPE
-          if (j + 2 < w.total) qk_step(j + 3 == w.total);  // F(j+1) arrives after P(j): PV first
-#endif
+          if (j + 2 < nt) qk_step(j + 3 == nt);  // F(j+1) arrives after P(j): PV first
         }
       }
     }
   } else if (warp == 2) {
     setmaxnreg_dec<kRegsCtl>();
-#if CSA_ROW_SPLIT == 2
-  } else {
-    // =========================================================================================== softmax (2 thr/row)
-    setmaxnreg_inc<kRegsSoftmax>();
-    const int sw = warp - 4;                    // 0..15
-    const int quarter = sw & 3;                 // TMEM lane quarter (== warp % 4)
-    const int s = (sw >> 2) & 1;                // Q tile
-    const int half = sw >> 3;                   // which 64 score columns / 32 output columns of the row
-    const int row = (quarter << 5) | lane;      // query row inside the tile == TMEM lane
-    const uint32_t lane_base = static_cast<uint32_t>(quarter << 5) << 16;
-    const uint32_t tS = tmem + lane_base + kColS + s * kBN + half * (kBN / 2);
-    const uint32_t tO = tmem + lane_base + kColO + s * kHD + half * (kHD / 2);
-    const uint32_t tP = tmem + lane_base + kColP + s * (kBN / 2) + half * (kBN / 4);
-    const uint32_t bar_s = (SB(s_full) + 8u * (s));
-    const uint32_t bar_f = (SB(s_free) + 8u * (s));
-    const uint32_t bar_p = (SB(p_ready) + 8u * (s));
-    const uint32_t bar_o = (SB(o_done) + 8u * (s));
-    const int pair_bar = 1 + s * 4 + quarter;   // named barrier shared by the two warps that own these 32 rows
-    const float sc = p.scale_log2;
-    const uint64_t sc2 = pack_f2(sc, sc);
-    uint32_t sph = 0;
-    uint32_t od = 0;  // PV completions on o_done[s] before the current unit
-#if CSA_PINGPONG
-    // exp token between the two Q tiles, handed over by whole warpgroup pairs (named barriers 9 and 10)
-    const int tok_in = 9 + (s ^ 1);
-    const int tok_out = 9 + s;
-    bool have_token = (s == 0);
-#endif
-
-    if (lane == 0) mbar_arrive(bar_f);  // S is free before the first QK of the kernel
-
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const Unit w = decode_unit(p, u);
-      const int q_in_frame = w.qp * (2 * kBM) + s * kBM + row;
-      const bool row_ok = q_in_frame < p.n_q;
-      uint4* optr = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
-                                             static_cast<int64_t>(w.q_row0 + s * kBM + row) * p.o_ld + w.h * kHD +
-                                             half * (kHD / 2));
-      if (w.total == 0) {
-        if (row_ok) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) optr[i] = make_uint4(0, 0, 0, 0);
-        }
-        continue;
-      }
-      float m = -INFINITY;  // running max of the WHOLE row, already multiplied by scale*log2(e)
-      float l = 0.f;        // running sum of this thread's 64 columns
-      TileWalker walk;
-      walk.init(w);
-
-      for (int j = 0; j < w.total; ++j) {
-        mbar_wait(bar_s, sph, 0x300 + s, p.dbg);
-        sph ^= 1;
-        tc_fence_after();
-        uint32_t sv[2][32];
-        tmem_ld32(tS + 0, sv[0]);
-        tmem_ld32(tS + 32, sv[1]);
-        tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_f);  // this warp's share of S is in registers
-
-        const int valid = walk.next() - half * (kBN / 2);
-        if (valid < kBN / 2) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
-        }
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            mx[(i >> 1) & 3] = fmax3(mx[(i >> 1) & 3], __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
-        const float mine = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        // exchange the partial maxima with the thread that owns the other 64 columns of this row
-        sm.xch_max[s][j & 1][half][row] = mine;
-        named_bar_sync(pair_bar, 64);
-        const float other = sm.xch_max[s][j & 1][half ^ 1][row];
-        const float m_new = fmaxf(m, fmaxf(mine, other) * sc);
-
-        if (j == 0) {
-          m = m_new;
-        } else {
-          // P and O of this Q tile are still being read by the PV of tile j-1 until o_done completes
-          mbar_wait(bar_o, (od + j - 1) & 1, 0x310 + s, p.dbg);
-          tc_fence_after();
-          const bool need = m_new > m + 8.0f;  // identical in both threads of the row
-          if (__any_sync(0xffffffffu, need)) {
-            const float alpha = need ? fast_exp2(m - m_new) : 1.0f;
-            if (need) m = m_new;
-            l *= alpha;
-            uint32_t ov[32];
-            tmem_ld32(tO, ov);  // this thread's 32 output columns
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st32(tO, ov);
-          }
-        }
-
-        uint64_t nm2 = pack_f2(-m, -m);
-        uint64_t ls[2] = {0ull, 0ull};
-#if CSA_PINGPONG
-        if (have_token) {
-          have_token = false;
-        } else {
-          named_bar_sync(tok_in, 512);
-        }
-        asm volatile("" : "+l"(nm2));  // every exponential depends on nm2: none may be hoisted above the token
-#endif
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const uint64_t x2 =
-                ffma2(pack_f2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
-            float p0, p1;
-            if (poly_pair(i)) {
-              poly_exp2_x2(x2, p0, p1);
-            } else {
-              float x0, x1;
-              unpack_f2(x2, x0, x1);
-              p0 = fast_exp2(x0);
-              p1 = fast_exp2(x1);
-            }
-            ls[i & 1] = fadd2(ls[i & 1], pack_f2(p0, p1));
-            pk[i] = pack2<kBF16>(p0, p1);
-          }
-          tmem_st16(tP + c * 16, pk);
-#if CSA_PINGPONG
-          if (c == (CSA_TOKEN_CHUNK >= 2 ? 1 : 0)) named_bar_arrive(tok_out, 512);
-#endif
-        }
-        {
-          float a0, a1, b0, b1;
-          unpack_f2(ls[0], a0, a1);
-          unpack_f2(ls[1], b0, b1);
-          l += (a0 + a1) + (b0 + b1);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p);
-      }
-
-      // epilogue: wait for the last PV, add the two partial row sums, normalise and store this thread's 32 columns
-      mbar_wait(bar_o, (od + w.total - 1) & 1, 0x320 + s, p.dbg);
-      tc_fence_after();
-      od += w.total;
-      sm.xch_sum[s][half][row] = l;
-      named_bar_sync(pair_bar, 64);
-      const float inv = 1.0f / (l + sm.xch_sum[s][half ^ 1][row]);
-      {
-        uint32_t ov[32];
-        tmem_ld32(tO, ov);
-        tc_wait_ld();
-        if (row_ok) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 v4;
-            v4.x = pack2<kBF16>(__uint_as_float(ov[8 * i + 0]) * inv, __uint_as_float(ov[8 * i + 1]) * inv);
-            v4.y = pack2<kBF16>(__uint_as_float(ov[8 * i + 2]) * inv, __uint_as_float(ov[8 * i + 3]) * inv);
-            v4.z = pack2<kBF16>(__uint_as_float(ov[8 * i + 4]) * inv, __uint_as_float(ov[8 * i + 5]) * inv);
-            v4.w = pack2<kBF16>(__uint_as_float(ov[8 * i + 6]) * inv, __uint_as_float(ov[8 * i + 7]) * inv);
-            optr[i] = v4;
-          }
-        }
-      }
-      tc_fence_before();
-      named_bar_sync(pair_bar, 64);  // xch_sum may be rewritten by the next unit only after both threads read it
-    }
-#if CSA_PINGPONG
-    if (s == 0 && !have_token) named_bar_sync(tok_in, 512);  // absorb Q tile 1's last hand-over
-#endif
-  }
-#else
   } else {
     // =========================================================================================== softmax
     setmaxnreg_inc<kRegsSoftmax>();
@@ -714,188 +534,29 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
 
     if (lane == 0) mbar_arrive(bar_f);  // S is free before the first QK of the kernel
 
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    for (int u = blockIdx.x; u < p.n_sched; u += gridDim.x) {
       const Unit w = decode_unit(p, u);
+      const int nt = w.nt;
       const int q_in_frame = w.qp * (2 * kBM) + s * kBM + row;
       const bool row_ok = q_in_frame < p.n_q;
       uint4* optr = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
                                              static_cast<int64_t>(w.q_row0 + s * kBM + row) * p.o_ld + w.h * kHD);
       TRACE(10);
-      if (w.total == 0) {
-        if (row_ok) {
+      if (w.total == 0) {  // no key at all (never split: every piece of such a unit lands here)
+        if (row_ok && (w.piece < 0 || w.t0 == 0)) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) optr[i] = make_uint4(0, 0, 0, 0);
         }
         continue;
       }
-#if CSA_SOFTMAX_PIPE
-      float m = -INFINITY;  // running max, already multiplied by scale*log2(e)
-      float l = 0.f;
-      uint32_t sv[4][32];  // the score row of the tile being exponentiated; refilled in place with the next tile's
-      float mx[4];         // partial row maxima (unscaled) of the tile held in sv
-      TileWalker walk;
-      walk.init(w);
-
-      // masks the keys beyond `valid` of chunk c and folds the chunk into the partial maxima
-      auto chunk_max = [&](const int c, const int valid) {
-        if (valid < kBN) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          mx[(i >> 1) & 3] = fmax3(mx[(i >> 1) & 3], __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
-      };
-
-      // prologue: scores of the unit's first tile
-      mbar_wait(bar_s, sph, 0x300 + s, p.dbg);
-      sph ^= 1;
-      tc_fence_after();
-      tmem_ld32(tS + 0, sv[0]);
-      tmem_ld32(tS + 32, sv[1]);
-      tmem_ld32(tS + 64, sv[2]);
-      tmem_ld32(tS + 96, sv[3]);
-      tc_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_f);  // S may be overwritten with the next tile's scores
-      {
-        const int valid0 = walk.next();
-        mx[0] = mx[1] = mx[2] = mx[3] = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) chunk_max(c, valid0);
-      }
-
-      for (int j = 0; j < w.total; ++j) {
-        const float m_new = fmaxf(m, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sc);
-        TRACE(4);
-        // Everything the exp phase will wait for is checked before the token is taken (a token holder that stalls
-        // blocks both Q tiles): the PV of tile j-1 (it reads P and O of this Q tile) and the scores of tile j+1.
-        if (j == 0) {
-          m = m_new;
-        } else {
-          mbar_wait(bar_o, (od + j - 1) & 1, 0x310 + s, p.dbg);
-          tc_fence_after();
-          const bool need = m_new > m + 8.0f;
-          if (__any_sync(0xffffffffu, need)) {
-            const float alpha = need ? fast_exp2(m - m_new) : 1.0f;
-            if (need) m = m_new;
-            l *= alpha;
-            uint32_t ov[32];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              tmem_ld32(tO + c * 32, ov);
-              tc_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-              tmem_st32(tO + c * 32, ov);
-            }
-          }
-        }
-        const bool more = (j + 1 < w.total);
-        int valid_n = kBN;
-        if (more) {
-          valid_n = walk.next();
-          mbar_wait(bar_s, sph, 0x301 + s, p.dbg);
-          sph ^= 1;
-          tc_fence_after();
-        }
-        TRACE(5);
-
-        // Software pipeline: while the MUFU works through chunk c of tile j, chunk c of S(j+1) — computed by the
-        // tensor core since S(j) was released — is pulled into the registers chunk c just vacated, and its row
-        // max is folded in one chunk later.
-        mx[0] = mx[1] = mx[2] = mx[3] = -INFINITY;
-        uint64_t nm2 = pack_f2(-m, -m);
-        uint64_t ls[2] = {0ull, 0ull};
-#if CSA_PINGPONG
-        if (have_token) {
-          have_token = false;
-        } else {
-          named_bar_sync(tok_in, 64);  // the other Q tile's warp on this sub-partition has issued its exponentials
-        }
-        asm volatile("" : "+l"(nm2));  // every exponential depends on nm2: none may be hoisted above the token
-#endif
-        TRACE(6);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint64_t xs[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            xs[i] = ffma2(pack_f2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
-          if (more) {
-            if (c > 0) {
-              tc_wait_ld();
-              chunk_max(c - 1, valid_n);
-            }
-            tmem_ld32(tS + c * 32, sv[c]);  // the chunk's scores are consumed: refill with the next tile's
-          }
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0, p1;
-            if (poly_pair(i)) {
-              poly_exp2_x2(xs[i], p0, p1);
-            } else {
-              float x0, x1;
-              unpack_f2(xs[i], x0, x1);
-              p0 = fast_exp2(x0);
-              p1 = fast_exp2(x1);
-            }
-            ls[i & 1] = fadd2(ls[i & 1], pack_f2(p0, p1));
-            pk[i] = pack2<kBF16>(p0, p1);
-          }
-          tmem_st16(tP + c * 16, pk);
-#if CSA_PINGPONG
-          if (c == CSA_TOKEN_CHUNK) named_bar_arrive(tok_out, 64);  // the other Q tile may start its exponentials
-#endif
-        }
-        TRACE(7);
-        if (more) {
-          tc_wait_ld();
-          chunk_max(3, valid_n);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_f);
-        }
-        {
-          float a0, a1, b0, b1;
-          unpack_f2(ls[0], a0, a1);
-          unpack_f2(ls[1], b0, b1);
-          l += (a0 + a1) + (b0 + b1);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p);
-        TRACE(8);
-      }
-
-#else
       float m = -INFINITY;  // running max, already multiplied by scale*log2(e)
       float l = 0.f;
       TileWalker walk;
       walk.init(w);
+      for (int t = 0; t < w.t0; ++t) walk.next();
       uint32_t sv[4][32];  // the score row of the current tile (a thread owns a whole 128-key row)
 
-#if CSA_EARLY_LD
-      // scores of the unit's first tile; later tiles are pulled during the exp phase of their predecessor
-      mbar_wait(bar_s, sph, 0x300 + s, p.dbg);
-      sph ^= 1;
-      tc_fence_after();
-      tmem_ld32(tS + 0, sv[0]);
-      tmem_ld32(tS + 32, sv[1]);
-      tmem_ld32(tS + 64, sv[2]);
-      tmem_ld32(tS + 96, sv[3]);
-      tc_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_f);
-#endif
-
-      for (int j = 0; j < w.total; ++j) {
-#if !CSA_EARLY_LD
+      for (int j = 0; j < nt; ++j) {
         TRACE(1);
         mbar_wait(bar_s, sph, 0x300 + s, p.dbg);
         sph ^= 1;
@@ -911,7 +572,6 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_f);
         TRACE(3);
-#endif
 
         const int valid = walk.next();
         if (valid < kBN) {
@@ -921,38 +581,31 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
             for (int i = 0; i < 32; ++i)
               if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
         }
-        // row max: 4 independent chains of 3-input max
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        // row max: 8 independent chains of 3-input max (8 deep each), then a 3-input tree
+        float mx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; i += 2)
-            mx[(i >> 1) & 3] = fmax3(mx[(i >> 1) & 3], __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
-        const float m_new = fmaxf(m, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sc);
+            mx[(i >> 1) & 7] = fmax3(mx[(i >> 1) & 7], __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+        const float m_new =
+            fmaxf(m, fmax3(fmax3(mx[0], mx[1], mx[2]), fmax3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])) * sc);
 #if CSA_TRACE
         asm volatile("" ::"f"(m_new));
         TRACE(4);
 #endif
 
-        // P and O of this Q tile are still being read by the PV of tile j-1 until o_done completes.
-        // CSA_DEFER_ODONE=1 moves the wait of the common case (no rescale of O) to just before the first P store;
-        // measured slower with the exp token: a token holder that stalls blocks both Q tiles.
-        bool pv_pending = (j > 0);
+        // P and O of this Q tile are still being read by the PV of tile j-1 until o_done completes.  The wait sits
+        // before the exp token is taken: a token holder that stalls blocks both Q tiles.
         if (j == 0) {
           m = m_new;
         } else {
           const bool need = m_new > m + 8.0f;
-#if !CSA_DEFER_ODONE
           mbar_wait(bar_o, (od + j - 1) & 1, 0x310 + s, p.dbg);
           tc_fence_after();
-          pv_pending = false;
-#endif
           if (__any_sync(0xffffffffu, need)) {
-#if CSA_DEFER_ODONE
-            mbar_wait(bar_o, (od + j - 1) & 1, 0x310 + s, p.dbg);
-            tc_fence_after();
-            pv_pending = false;
-#endif
             const float alpha = need ? fast_exp2(m - m_new) : 1.0f;
             if (need) m = m_new;
             l *= alpha;
@@ -969,15 +622,6 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         }
 
         TRACE(5);
-        const bool more = j + 1 < w.total;
-#if CSA_EARLY_LD == 1
-        // S(j+1) was issued when S(j) was released
-        if (more) {
-          mbar_wait(bar_s, sph, 0x301 + s, p.dbg);
-          sph ^= 1;
-          tc_fence_after();
-        }
-#endif
 
         // P = exp2(S*scale - m) in chunks of 32 keys: FFMA2 -> MUFU.EX2 -> FADD2 row sum -> pack -> TMEM
         uint64_t nm2 = pack_f2(-m, -m);
@@ -997,10 +641,6 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             xs[i] = ffma2(pack_f2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
-#if CSA_EARLY_LD == 1
-          // the chunk's scores are consumed: refill its registers with the next tile's scores while the MUFU works
-          if (more) tmem_ld32(tS + c * 32, sv[c]);
-#endif
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -1016,28 +656,11 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
             ls[i & 1] = fadd2(ls[i & 1], pack_f2(p0, p1));
             pk[i] = pack2<kBF16>(p0, p1);
           }
-          if (c == 0 && pv_pending) {
-            mbar_wait(bar_o, (od + j - 1) & 1, 0x311 + s, p.dbg);
-            tc_fence_after();
-          }
           tmem_st16(tP + c * 16, pk);
 #if CSA_PINGPONG
           if (c == CSA_TOKEN_CHUNK) named_bar_arrive(tok_out, 64);  // the other Q tile may start its exponentials
 #endif
         }
-#if CSA_EARLY_LD == 2
-        // all exponentials are issued: pull the next tile's scores (computed since S(j) was released, an exp phase
-        // ago) so that the TMEM read latency overlaps the P store drain and the p_ready hand-over
-        if (more) {
-          mbar_wait(bar_s, sph, 0x301 + s, p.dbg);
-          sph ^= 1;
-          tc_fence_after();
-          tmem_ld32(tS + 0, sv[0]);
-          tmem_ld32(tS + 32, sv[1]);
-          tmem_ld32(tS + 64, sv[2]);
-          tmem_ld32(tS + 96, sv[3]);
-        }
-#endif
         TRACE(7);
         {
           float a0, a1, b0, b1;
@@ -1050,50 +673,113 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p);
         TRACE(8);
-#if CSA_EARLY_LD
-        if (more) {
-          // the next score row now lives in registers: let the tensor core overwrite S
-          tc_wait_ld();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_f);
-        }
-#endif
       }
 
-#endif
-      // epilogue: wait for the last PV, normalise, store
+      // epilogue: wait for the last PV
       TRACE(11);
-      mbar_wait(bar_o, (od + w.total - 1) & 1, 0x320 + s, p.dbg);
-      tc_fence_after();
+      if (nt > 0) {
+        mbar_wait(bar_o, (od + nt - 1) & 1, 0x320 + s, p.dbg);
+        tc_fence_after();
+      }
       TRACE(12);
-      od += w.total;
-      const float inv = 1.0f / l;
+      od += nt;
+      if (w.piece < 0) {
+        // whole unit: normalise, store
+        const float inv = 1.0f / l;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t ov[32];
-        tmem_ld32(tO + c * 32, ov);
-        tc_wait_ld();
-        if (row_ok) {
+        for (int c = 0; c < 2; ++c) {
+          uint32_t ov[32];
+          tmem_ld32(tO + c * 32, ov);
+          tc_wait_ld();
+          if (row_ok) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 v4;
-            v4.x = pack2<kBF16>(__uint_as_float(ov[8 * i + 0]) * inv, __uint_as_float(ov[8 * i + 1]) * inv);
-            v4.y = pack2<kBF16>(__uint_as_float(ov[8 * i + 2]) * inv, __uint_as_float(ov[8 * i + 3]) * inv);
-            v4.z = pack2<kBF16>(__uint_as_float(ov[8 * i + 4]) * inv, __uint_as_float(ov[8 * i + 5]) * inv);
-            v4.w = pack2<kBF16>(__uint_as_float(ov[8 * i + 6]) * inv, __uint_as_float(ov[8 * i + 7]) * inv);
-            optr[c * 4 + i] = v4;
+            for (int i = 0; i < 4; ++i) {
+              uint4 v4;
+              v4.x = pack2<kBF16>(__uint_as_float(ov[8 * i + 0]) * inv, __uint_as_float(ov[8 * i + 1]) * inv);
+              v4.y = pack2<kBF16>(__uint_as_float(ov[8 * i + 2]) * inv, __uint_as_float(ov[8 * i + 3]) * inv);
+              v4.z = pack2<kBF16>(__uint_as_float(ov[8 * i + 4]) * inv, __uint_as_float(ov[8 * i + 5]) * inv);
+              v4.w = pack2<kBF16>(__uint_as_float(ov[8 * i + 6]) * inv, __uint_as_float(ov[8 * i + 7]) * inv);
+              optr[c * 4 + i] = v4;
+            }
           }
         }
+        tc_fence_before();
+      } else {
+        // piece of a split unit: leave the unnormalised partial (O, m, l) of this row in the workspace; the CTA
+        // that delivers the last piece of the unit (arrival counter) merges all of them — nobody waits for anybody
+        const int prow = s * kBM + row;
+        float* part = p.ws + static_cast<int64_t>(w.piece) * kPieceFloats;
+        if (nt > 0) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t ov[32];
+            tmem_ld32(tO + c * 32, ov);
+            tc_wait_ld();
+            uint4* dst = reinterpret_cast<uint4*>(part + prow * kHD + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) __stcg(dst + i, make_uint4(ov[4 * i], ov[4 * i + 1], ov[4 * i + 2], ov[4 * i + 3]));
+          }
+          tc_fence_before();
+        }
+        __stcg(part + 2 * kBM * kHD + prow, m);
+        __stcg(part + 2 * kBM * kHD + 2 * kBM + prow, l);
+        __threadfence();
+        named_bar_sync(9, kThreads - 128);  // all softmax threads of the CTA have published their rows
+        if (threadIdx.x == 128) {
+          const uint32_t prev = atomicAdd(p.ws_count + w.split_unit, 1u);
+          const bool last = prev == static_cast<uint32_t>(p.split) - 1u;
+          if (last) p.ws_count[w.split_unit] = 0u;  // ready for the next launch
+          sm.merge_flag = last ? 1u : 0u;
+        }
+        named_bar_sync(9, kThreads - 128);
+        if (sm.merge_flag != 0u) {
+          __threadfence();
+          const float* base = p.ws + static_cast<int64_t>(w.piece - (w.piece % p.split)) * kPieceFloats;
+          float mm = -INFINITY;
+          for (int i = 0; i < p.split; ++i)
+            mm = fmaxf(mm, __ldcg(base + static_cast<int64_t>(i) * kPieceFloats + 2 * kBM * kHD + prow));
+          float acc[kHD];
+#pragma unroll
+          for (int c = 0; c < kHD; ++c) acc[c] = 0.f;
+          float lsum = 0.f;
+          for (int i = 0; i < p.split; ++i) {
+            const float* pi = base + static_cast<int64_t>(i) * kPieceFloats;
+            const float li = __ldcg(pi + 2 * kBM * kHD + 2 * kBM + prow);
+            if (li > 0.f) {  // a piece without key tiles contributes nothing (its O rows were never written)
+              const float wgt = fast_exp2(__ldcg(pi + 2 * kBM * kHD + prow) - mm);
+              lsum += wgt * li;
+              const float4* src = reinterpret_cast<const float4*>(pi + prow * kHD);
+#pragma unroll
+              for (int c = 0; c < kHD / 4; ++c) {
+                const float4 x = __ldcg(src + c);
+                acc[4 * c + 0] += wgt * x.x;
+                acc[4 * c + 1] += wgt * x.y;
+                acc[4 * c + 2] += wgt * x.z;
+                acc[4 * c + 3] += wgt * x.w;
+              }
+            }
+          }
+          if (row_ok) {
+            const float inv = lsum > 0.f ? 1.0f / lsum : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4 v4;
+              v4.x = pack2<kBF16>(acc[8 * i + 0] * inv, acc[8 * i + 1] * inv);
+              v4.y = pack2<kBF16>(acc[8 * i + 2] * inv, acc[8 * i + 3] * inv);
+              v4.z = pack2<kBF16>(acc[8 * i + 4] * inv, acc[8 * i + 5] * inv);
+              v4.w = pack2<kBF16>(acc[8 * i + 6] * inv, acc[8 * i + 7] * inv);
+              optr[i] = v4;
+            }
+          }
+        }
+        named_bar_sync(9, kThreads - 128);  // merge_flag may be rewritten by the next piece only after everyone read it
       }
-      tc_fence_before();
     }
 #if CSA_PINGPONG
     // Q tile 1's last hand-over has no taker: absorb it so that no barrier is left half-arrived at exit
     if (s == 0 && !have_token) named_bar_sync(tok_in, 64);
 #endif
   }
-#endif
 
   __syncthreads();
   if (warp == 2) {
@@ -1102,429 +788,6 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
   }
 }
 
-
-// =================================================================================================================
-// Half-tile organisation.  TMEM holds, per Q tile, two 64-key score buffers, two P buffers and O:
-//   Q tile s at column 256*s:  S[0] +0, S[1] +64 | P[0] +128, P[1] +160 (64 16-bit values = 32 columns) | O +192.
-// Double buffering removes both couplings of the 128-key organisation (S(j+1) cannot be produced before S(j) is
-// read; P(j+1) cannot be written before PV(j) has drained), which is what allows a softmax thread to read and
-// reduce the next half tile's scores *inside* the MUFU-bound exponential block of the current one.
-// Half tile g (a per-Q-tile counter that runs across units) uses buffer g & 1; every barrier below completes once
-// per use of its buffer, so the parity a role waits for is a function of g alone.
-constexpr int kHN = 64;  // keys per half tile
-
-// Walks the 64-key half tiles of a unit in order.  Segments (gathered list, A run 1, A run 2, B run) are padded to
-// whole 128-key smem tiles by the producer, so a segment of L keys has ceil(L/64) half tiles and half tile i of a
-// segment lives in rows [64 * (i & 1), +64) of smem tile i / 2 of that segment.
-struct HalfWalker {
-  int l1, l2, l3;  // lengths of the segments after the current one
-  int rem;         // keys left in the current segment
-  int h;           // which half of its smem tile the next half tile is
-  __device__ __forceinline__ void skip_empty() {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      if (rem <= 0) {
-        rem = l1;
-        l1 = l2;
-        l2 = l3;
-        l3 = 0;
-      }
-    }
-  }
-  __device__ __forceinline__ void init(const Unit& w) {
-    rem = w.ng;
-    l1 = w.seg_len[0];
-    l2 = w.seg_len[1];
-    l3 = w.seg_len[2];
-    h = 0;
-    skip_empty();
-  }
-  // valid keys of the next half tile; `half` = its half of the smem tile, `last` = it is the last one of that tile
-  __device__ __forceinline__ int next(int& half, bool& last) {
-    const int v = rem < kHN ? rem : kHN;
-    half = h;
-    rem -= kHN;
-    last = (h == 1) || (rem <= 0);
-    h = last ? 0 : 1;
-    skip_empty();
-    return v;
-  }
-  __device__ __forceinline__ int next() {
-    int half;
-    bool last;
-    return next(half, last);
-  }
-};
-
-__device__ __forceinline__ int unit_halves(const Unit& w) {
-  int n = (w.ng + kHN - 1) / kHN;
-#pragma unroll
-  for (int i = 0; i < kMaxSeg; ++i) n += (w.seg_len[i] + kHN - 1) / kHN;
-  return n;
-}
-
-template <bool kBF16>
-__global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel_h64(const __grid_constant__ AttnKernelParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  AttnSmem& sm = *reinterpret_cast<AttnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t sb = smem_u32(&sm);
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tm_q);
-    tma_prefetch_desc(&p.tm_ka);
-    tma_prefetch_desc(&p.tm_va);
-    tma_prefetch_desc(&p.tm_kag);
-    tma_prefetch_desc(&p.tm_vag);
-    tma_prefetch_desc(&p.tm_kb);
-    tma_prefetch_desc(&p.tm_vb);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init((SB(q_full) + 8u * (i)), 1);
-      mbar_init((SB(q_empty) + 8u * (i)), 1);
-      for (int b = 0; b < 2; ++b) {
-        mbar_init((SB(h_s_full) + 8u * (2 * i + b)), 1);
-        mbar_init((SB(h_s_free) + 8u * (2 * i + b)), 4);   // one arrival per softmax warp of the Q tile
-        mbar_init((SB(h_p_ready) + 8u * (2 * i + b)), 4);
-        mbar_init((SB(h_pv_done) + 8u * (2 * i + b)), 1);
-      }
-    }
-    for (int i = 0; i < kKStages; ++i) {
-      mbar_init((SB(k_full) + 8u * (i)), 1);
-      mbar_init((SB(k_empty) + 8u * (i)), 2);  // one commit per MMA stream
-    }
-    for (int i = 0; i < kVStages; ++i) {
-      mbar_init((SB(v_full) + 8u * (i)), 1);
-      mbar_init((SB(v_empty) + 8u * (i)), 2);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc<512>(SB(tmem_base));
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = sm.tmem_base;
-
-  if (warp == 0) {
-    setmaxnreg_dec<kRegsCtl>();
-    producer_warp(p, sb, lane);
-  } else if (warp == 1 || warp == 3) {
-    // =========================================================================================== MMA issue
-    // One warp per Q tile, warp-uniform control flow, one elected lane issues.  Per unit: QK(0), QK(1), then
-    // { QK(i+2), PV(i) }: the scores run two half tiles ahead, so S(i+1) is in TMEM a whole exponential block
-    // before the softmax threads want it.
-    setmaxnreg_dec<kRegsCtl>();
-    const int s = __shfl_sync(0xffffffffu, warp >> 1, 0);
-    constexpr uint32_t idesc_qk = make_idesc(kBM, kHN, kBF16 ? 1 : 0, 0, 0);
-    constexpr uint32_t idesc_pv = make_idesc(kBM, kHD, kBF16 ? 1 : 0, 0, 1);
-    const uint32_t tbase = tmem + s * 256;
-    const uint32_t bar_qf = (SB(q_full) + 8u * (s)), bar_qe = (SB(q_empty) + 8u * (s));
-    const uint32_t bar_sfull = SB(h_s_full) + 16u * s, bar_sfree = SB(h_s_free) + 16u * s;
-    const uint32_t bar_pready = SB(h_p_ready) + 16u * s, bar_pvdone = SB(h_pv_done) + 16u * s;
-    const uint64_t dq = make_sw128_desc((SB(q) + static_cast<uint32_t>(kTileBytes) * (s)));
-    int ks = 0, vs = 0;
-    uint32_t kph = 0, vph = 0, qph = 0;
-    uint32_t gq = 0, gp = 0;  // half tiles whose QK / PV has been issued, over the whole kernel
-    TRACE_INIT(2 + s, lane == 0);
-
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const Unit w = decode_unit(p, u);
-      if (w.total == 0) continue;
-      const int n = unit_halves(w);
-      HalfWalker wq, wp;
-      wq.init(w);
-      wp.init(w);
-      int iq = 0;  // half tiles of this unit whose QK has been issued
-
-      auto qk_step = [&]() {
-        int half;
-        bool last;
-        wq.next(half, last);
-        const uint32_t b = gq & 1u;
-        TRACE(20);
-        if (half == 0) mbar_wait((SB(k_full) + 8u * (ks)), kph, 0x201 + s, p.dbg);
-        mbar_wait(bar_sfree + 8u * b, ((gq >> 1) & 1u) ^ 1u, 0x203 + s, p.dbg);  // S[b] has been read (half tile gq-2)
-        tc_fence_after();
-        TRACE(22);
-        const uint64_t dk =
-            make_sw128_desc((SB(k) + static_cast<uint32_t>(kTileBytes) * (ks)) + static_cast<uint32_t>(half) * (kHN * 128));
-        if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < kHD / 16; ++kk) mma_ss(tbase + b * kHN, dq + kk * 2, dk + kk * 2, idesc_qk, kk > 0 ? 1u : 0u);
-          tc_commit(bar_sfull + 8u * b);
-          if (last) tc_commit((SB(k_empty) + 8u * (ks)));
-          if (iq == n - 1) tc_commit(bar_qe);
-        }
-        __syncwarp();
-        if (last) {
-          if (++ks == kKStages) { ks = 0; kph ^= 1; }
-        }
-        ++gq;
-        ++iq;
-      };
-
-      mbar_wait(bar_qf, qph, 0x200 + s, p.dbg);
-      qph ^= 1;
-      qk_step();
-      if (n > 1) qk_step();
-      for (int i = 0; i < n; ++i) {
-        if (i + 2 < n) qk_step();
-        int half;
-        bool last;
-        wp.next(half, last);
-        const uint32_t b = gp & 1u;
-        TRACE(23);
-        if (half == 0) mbar_wait((SB(v_full) + 8u * (vs)), vph, 0x210 + s, p.dbg);
-        mbar_wait(bar_pready + 8u * b, (gp >> 1) & 1u, 0x212 + s, p.dbg);
-        tc_fence_after();
-        TRACE(25);
-        const uint64_t dv =
-            make_sw128_desc((SB(v) + static_cast<uint32_t>(kTileBytes) * (vs)) + static_cast<uint32_t>(half) * (kHN * 128));
-        if (elect_one()) {
-#pragma unroll
-          for (int kk = 0; kk < kHN / 16; ++kk) {
-            // 16 keys = 16 rows of 128 B along the contraction dim (MN-major B); 16 16-bit P values = 8 columns
-            mma_ts(tbase + 192, tbase + 128 + b * 32 + kk * 8, dv + kk * (2048 >> 4), idesc_pv,
-                   (i > 0 || kk > 0) ? 1u : 0u);
-          }
-          tc_commit(bar_pvdone + 8u * b);
-          if (last) tc_commit((SB(v_empty) + 8u * (vs)));
-        }
-        __syncwarp();
-        TRACE(26);
-        if (last) {
-          if (++vs == kVStages) { vs = 0; vph ^= 1; }
-        }
-        ++gp;
-      }
-    }
-  } else if (warp == 2) {
-    setmaxnreg_dec<kRegsCtl>();
-  } else {
-    // =========================================================================================== softmax
-    // Thread == query row.  Steady state of one step (half tile g in `cur`, already masked, its row max folded
-    // into m): pull S(g+1) into `nxt` (tcgen05.ld, asynchronous), exponentiate the first 32 keys of `cur`, then
-    // in ONE basic block exponentiate the other 32 keys and reduce the row max of `nxt` — the FMNMX3 chain fills
-    // issue slots the MUFU-paced exponentials leave empty.  P(g) goes to its own TMEM buffer, so nothing here waits
-    // for the PV of the previous half tile, and S(g+1) was produced during the previous step.
-    setmaxnreg_inc<kRegsSoftmax>();
-    const int s = (warp - 4) >> 2;
-    const int row = ((warp & 3) << 5) | lane;
-    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) << 5) << 16;
-    const uint32_t tbase = tmem + lane_base + s * 256;
-    const uint32_t bar_sfull = SB(h_s_full) + 16u * s, bar_sfree = SB(h_s_free) + 16u * s;
-    const uint32_t bar_pready = SB(h_p_ready) + 16u * s, bar_pvdone = SB(h_pv_done) + 16u * s;
-    const float sc = p.scale_log2;
-    const uint64_t sc2 = pack_f2(sc, sc);
-    uint32_t g0 = 0;  // half tiles of earlier units
-#if CSA_PINGPONG
-    const int tok_in = 1 + 2 * (warp & 3) + (s ^ 1);
-    const int tok_out = 1 + 2 * (warp & 3) + s;
-    bool have_token = (s == 0);
-#endif
-    TRACE_INIT(s, (warp & 3) == 0 && lane == 0);
-
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const Unit w = decode_unit(p, u);
-      const int q_in_frame = w.qp * (2 * kBM) + s * kBM + row;
-      const bool row_ok = q_in_frame < p.n_q;
-      uint4* optr = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
-                                             static_cast<int64_t>(w.q_row0 + s * kBM + row) * p.o_ld + w.h * kHD);
-      if (w.total == 0) {
-        if (row_ok) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) optr[i] = make_uint4(0, 0, 0, 0);
-        }
-        continue;
-      }
-      const int n = unit_halves(w);
-      HalfWalker walk;
-      walk.init(w);
-      float m, l = 0.f;
-      uint32_t sva[2][32], svb[2][32];  // two half tiles of scores: the one being exponentiated and the next one
-
-      auto mask_tail = [&](uint32_t (&x)[2][32], const int valid) {
-        if (valid < kHN) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= valid) x[c][i] = 0xff800000u;  // -inf
-        }
-      };
-      auto row_max = [&](const uint32_t (&x)[2][32]) {
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            mx[(i >> 1) & 3] = fmax3(mx[(i >> 1) & 3], __uint_as_float(x[c][i]), __uint_as_float(x[c][i + 1]));
-        return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      };
-
-      // prologue: the unit's first half tile
-      {
-        const uint32_t b = g0 & 1u;
-        mbar_wait(bar_sfull + 8u * b, (g0 >> 1) & 1u, 0x300 + s, p.dbg);
-        tc_fence_after();
-        tmem_ld32(tbase + b * kHN + 0, sva[0]);
-        tmem_ld32(tbase + b * kHN + 32, sva[1]);
-        tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_sfree + 8u * b);
-        mask_tail(sva, walk.next());
-        m = row_max(sva) * sc;
-      }
-
-      // one step: exponentiate `cur` (half tile i of the unit), prefetch and reduce `nxt`
-      auto step = [&](uint32_t (&cur)[2][32], uint32_t (&nxt)[2][32], const int i) {
-        const uint32_t g = g0 + static_cast<uint32_t>(i);
-        const uint32_t b = g & 1u, bn = b ^ 1u;
-        const bool more = i + 1 < n;
-        TRACE(1);
-        if (more) mbar_wait(bar_sfull + 8u * bn, ((g + 1) >> 1) & 1u, 0x301 + s, p.dbg);  // S(g+1) is computed
-        mbar_wait(bar_pvdone + 8u * b, ((g >> 1) & 1u) ^ 1u, 0x310 + s, p.dbg);            // PV(g-2) has drained P[b]
-        tc_fence_after();
-        TRACE(2);
-        if (more) {
-          tmem_ld32(tbase + bn * kHN + 0, nxt[0]);
-          tmem_ld32(tbase + bn * kHN + 32, nxt[1]);
-        }
-        uint64_t nm2 = pack_f2(-m, -m);
-        uint64_t ls[2] = {0ull, 0ull};
-#if CSA_PINGPONG
-        if (have_token) {
-          have_token = false;
-        } else {
-          named_bar_sync(tok_in, 64);
-        }
-        asm volatile("" : "+l"(nm2));
-#endif
-        TRACE(6);
-        float mxn = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint64_t xs[16];
-#pragma unroll
-          for (int k2 = 0; k2 < 16; ++k2)
-            xs[k2] = ffma2(pack_f2(__uint_as_float(cur[c][2 * k2]), __uint_as_float(cur[c][2 * k2 + 1])), sc2, nm2);
-          if (c == 1 && more) {
-            // the next half tile's scores have landed (they were requested 32 exponentials ago)
-            tc_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_sfree + 8u * bn);
-            mask_tail(nxt, walk.next());
-          }
-          uint32_t pk[16];
-#pragma unroll
-          for (int k2 = 0; k2 < 16; ++k2) {
-            float p0, p1;
-            if (poly_pair(k2)) {
-              poly_exp2_x2(xs[k2], p0, p1);
-            } else {
-              float x0, x1;
-              unpack_f2(xs[k2], x0, x1);
-              p0 = fast_exp2(x0);
-              p1 = fast_exp2(x1);
-            }
-            ls[k2 & 1] = fadd2(ls[k2 & 1], pack_f2(p0, p1));
-            pk[k2] = pack2<kBF16>(p0, p1);
-          }
-          if (c == 1 && more) mxn = row_max(nxt);  // same basic block as the exponentials above
-          tmem_st16(tbase + 128 + b * 32 + c * 16, pk);
-#if CSA_PINGPONG
-          if (c == (CSA_TOKEN_CHUNK >= 2 ? 1 : 0)) named_bar_arrive(tok_out, 64);
-#endif
-        }
-        TRACE(7);
-        {
-          float a0, a1, b0, b1;
-          unpack_f2(ls[0], a0, a1);
-          unpack_f2(ls[1], b0, b1);
-          l += (a0 + a1) + (b0 + b1);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_pready + 8u * b);
-        TRACE(8);
-        if (more) {
-          // lazy rescale: only when the running max grows by more than 2^8 does O (and l) get rescaled — after the
-          // PV of this half tile has completed and before the next one can be issued (its p_ready comes later)
-          const float m_new = fmaxf(m, mxn * sc);
-          const bool need = m_new > m + 8.0f;
-          if (__any_sync(0xffffffffu, need)) {
-            mbar_wait(bar_pvdone + 8u * b, (g >> 1) & 1u, 0x311 + s, p.dbg);
-            tc_fence_after();
-            const float alpha = need ? fast_exp2(m - m_new) : 1.0f;
-            if (need) m = m_new;
-            l *= alpha;
-            uint32_t ov[32];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              tmem_ld32(tbase + 192 + c * 32, ov);
-              tc_wait_ld();
-#pragma unroll
-              for (int k2 = 0; k2 < 32; ++k2) ov[k2] = __float_as_uint(__uint_as_float(ov[k2]) * alpha);
-              tmem_st32(tbase + 192 + c * 32, ov);
-            }
-            tc_wait_st();
-            tc_fence_before();
-          }
-        }
-      };
-
-      for (int i = 0; i < n; i += 2) {
-        step(sva, svb, i);
-        if (i + 1 < n) step(svb, sva, i + 1);
-      }
-
-      // epilogue: wait for the last PV, normalise, store
-      {
-        const uint32_t gl = g0 + static_cast<uint32_t>(n) - 1u;
-        TRACE(11);
-        mbar_wait(bar_pvdone + 8u * (gl & 1u), (gl >> 1) & 1u, 0x320 + s, p.dbg);
-        tc_fence_after();
-        TRACE(12);
-      }
-      g0 += static_cast<uint32_t>(n);
-      const float inv = 1.0f / l;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t ov[32];
-        tmem_ld32(tbase + 192 + c * 32, ov);
-        tc_wait_ld();
-        if (row_ok) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 v4;
-            v4.x = pack2<kBF16>(__uint_as_float(ov[8 * i + 0]) * inv, __uint_as_float(ov[8 * i + 1]) * inv);
-            v4.y = pack2<kBF16>(__uint_as_float(ov[8 * i + 2]) * inv, __uint_as_float(ov[8 * i + 3]) * inv);
-            v4.z = pack2<kBF16>(__uint_as_float(ov[8 * i + 4]) * inv, __uint_as_float(ov[8 * i + 5]) * inv);
-            v4.w = pack2<kBF16>(__uint_as_float(ov[8 * i + 6]) * inv, __uint_as_float(ov[8 * i + 7]) * inv);
-            optr[c * 4 + i] = v4;
-          }
-        }
-      }
-      tc_fence_before();
-    }
-#if CSA_PINGPONG
-    if (s == 0 && !have_token) named_bar_sync(tok_in, 64);
-#endif
-  }
-
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem);
-  }
-}
 
 // ------------------------------------------------------------------------------------------------- host side
 static int encode_2d(CUtensorMap* tm, int dtype, const void* base, int64_t rows, int64_t cols, int64_t ld_elems,
@@ -1543,6 +806,8 @@ static int encode_2d(CUtensorMap* tm, int dtype, const void* base, int64_t rows,
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static thread_local int32_t g_last_launch[4] = {0, 0, 0, 0};  // {grid, n_whole, split, n_sched} of the last csa_attn_fwd
 
 }  // namespace csa
 
@@ -1634,15 +899,52 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
   if (ce != cudaSuccess) return set_error(static_cast<int>(ce), "cudaGetDevice: %s", cudaGetErrorString(ce));
   const int sms = sm_count(dev);
   if (sms <= 0) return set_error(CSA_E_DEVICE, "csa_attn_fwd: device %d is not sm_100", dev);
-  int grid = p.n_units < sms ? p.n_units : sms;
-  if (a->max_ctas > 0 && grid > a->max_ctas) grid = a->max_ctas;
+  int ctas = sms;
+  if (a->max_ctas > 0 && ctas > a->max_ctas) ctas = a->max_ctas;
+
+  // Tail split.  Units are dealt round-robin to `ctas` persistent CTAs; the last, partial round would keep only
+  // `rem` of them busy for a whole unit time.  Cutting each of those `rem` units into k pieces along the keys turns
+  // that round into ceil(rem * k / ctas) rounds of 1/k unit time.  k is the smallest value within 5 % of the best.
+  p.n_whole = p.n_units;
+  p.split = 1;
+  p.n_sched = p.n_units;
+  p.ws = nullptr;
+  p.ws_count = nullptr;
+  const int rem = p.n_units % ctas;
+  const int64_t piece_bytes = static_cast<int64_t>(kPieceFloats) * 4;
+  if (rem > 0 && a->workspace != nullptr && !(a->flags & CSA_ATTN_NO_SPLIT)) {
+    if (!aligned16(a->workspace)) return set_error(CSA_E_BADARG, "csa_attn_fwd: workspace must be 16-byte aligned");
+    const int64_t cap_pieces = (a->workspace_bytes - kWsHeaderBytes) / piece_bytes;
+    // an upper estimate of the key tiles of a unit: pieces of fewer than ~3 tiles are not worth their prologue
+    const int64_t est_keys = static_cast<int64_t>(a->ca_len) + a->cb_len + ((use_g || use_r) ? a->a_group_rows / 2 : 0);
+    const int k_cap = static_cast<int>(est_keys / (3 * kBN));
+    int best_k = 1;
+    double best_cost = 1.0;
+    for (int k = 2; k <= kMaxSplit && k <= k_cap; ++k) {
+      const int64_t pieces = static_cast<int64_t>(rem) * k;
+      if (pieces > cap_pieces || pieces > 2 * static_cast<int64_t>(ctas)) break;
+      const double cost = static_cast<double>((pieces + ctas - 1) / ctas) / k;
+      if (cost < best_cost * 0.95) {
+        best_cost = cost;
+        best_k = k;
+      }
+    }
+    if (best_k > 1 && rem * 4 <= kWsHeaderBytes) {
+      p.split = best_k;
+      p.n_whole = p.n_units - rem;
+      p.n_sched = p.n_whole + rem * best_k;
+      p.ws_count = static_cast<uint32_t*>(a->workspace);
+      p.ws = reinterpret_cast<float*>(static_cast<uint8_t*>(a->workspace) + kWsHeaderBytes);
+    }
+  }
+  const int grid = p.n_sched < ctas ? p.n_sched : ctas;
+  g_last_launch[0] = grid;
+  g_last_launch[1] = p.n_whole;
+  g_last_launch[2] = p.split;
+  g_last_launch[3] = p.n_sched;
 
   const size_t smem = sizeof(AttnSmem) + 1024;
-#if CSA_H64 && CSA_ROW_SPLIT == 1
-  auto kern = a->dtype == CSA_DTYPE_BF16 ? csa_attn_kernel_h64<true> : csa_attn_kernel_h64<false>;
-#else
   auto kern = a->dtype == CSA_DTYPE_BF16 ? csa_attn_kernel<true> : csa_attn_kernel<false>;
-#endif
   ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (ce != cudaSuccess)
     return set_error(static_cast<int>(ce), "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(ce));
@@ -1650,6 +952,22 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
   ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_error(static_cast<int>(ce), "csa_attn_kernel launch: %s", cudaGetErrorString(ce));
   return 0;
+}
+
+extern "C" int csa_debug_last_launch(int32_t* out4_host) {
+  if (!out4_host) return set_error(CSA_E_BADARG, "csa_debug_last_launch: null out");
+  for (int i = 0; i < 4; ++i) out4_host[i] = g_last_launch[i];
+  return 0;
+}
+
+extern "C" int64_t csa_attn_workspace_bytes(int32_t ctas) {
+  if (ctas <= 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    ctas = sm_count(dev);
+    if (ctas <= 0) return 0;
+  }
+  return kWsHeaderBytes + 2 * static_cast<int64_t>(ctas) * kPieceFloats * 4;
 }
 
 // Debug builds only (-DCSA_TRACE=1): device buffer of kTraceSlots * kTraceEvents 64-bit words for the timeline trace.

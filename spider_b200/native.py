@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CSA_B200_LIB: developer knob to load an experimental build of the same ABI (kernel tuning sweeps); default in-tree
 LIB_PATH = os.environ.get("CSA_B200_LIB") or os.path.join(_HERE, "libcsa_b200.so")
 
-CSA_ABI_VERSION = 2
+CSA_ABI_VERSION = 3
 CSA_DTYPE_F16 = 0
 CSA_DTYPE_BF16 = 1
 CSA_TILE = 128
@@ -38,6 +38,8 @@ EXPORTED_SYMBOLS = (
     "csa_sample_ranges",
     "csa_gather_kv",
     "csa_attn_fwd",
+    "csa_attn_workspace_bytes",
+    "csa_debug_last_launch",
 )
 
 
@@ -90,7 +92,12 @@ class CsaAttnArgs(ctypes.Structure):
         ("ranges", c_void_p),
         ("range_base", c_int32),
         ("range_step", c_int32),
+        ("workspace", c_void_p),
+        ("workspace_bytes", c_int64),
     ]
+
+
+CSA_ATTN_NO_SPLIT = 1
 
 
 _lib: Optional[ctypes.CDLL] = None
@@ -147,6 +154,10 @@ def load() -> ctypes.CDLL:
                                   c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]
     lib.csa_attn_fwd.restype = c_int32
     lib.csa_attn_fwd.argtypes = [POINTER(CsaAttnArgs), c_void_p]
+    lib.csa_debug_last_launch.restype = c_int32
+    lib.csa_debug_last_launch.argtypes = [POINTER(c_int32)]
+    lib.csa_attn_workspace_bytes.restype = c_int64
+    lib.csa_attn_workspace_bytes.argtypes = [c_int32]
 
     v = lib.csa_abi_version()
     if v != CSA_ABI_VERSION:
@@ -285,6 +296,25 @@ def gather_kv(k: torch.Tensor, v: torch.Tensor, group_rows: int, n_groups: int, 
     return k_s, v_s, out_group_rows
 
 
+# Tail-split scratch of csa_attn_fwd: one zero-initialised buffer per (device, stream) — launches on one stream are
+# ordered, so they can share it; the kernel leaves the header zero again.
+_WORKSPACES: dict = {}
+
+
+def attn_workspace(device: torch.device) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        with torch.cuda.device(device):
+            n = int(load().csa_attn_workspace_bytes(0))
+        if n <= 0:
+            raise CsaNativeError("csa_attn_workspace_bytes failed: " + (load().csa_last_error() or b"").decode())
+        ws = torch.zeros(n, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_frames: int, n_q: int,
              k_a: Optional[torch.Tensor] = None, v_a: Optional[torch.Tensor] = None, a_group_rows: int = 0,
              k_b: Optional[torch.Tensor] = None, v_b: Optional[torch.Tensor] = None, b_group_rows: int = 0,
@@ -292,7 +322,7 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
              list_base: int = -1, list_step: int = 0, g_adjust: int = 0,
              ca: tuple = (0, 0, 0), cb: tuple = (0, 0, 0), scale: Optional[float] = None,
              max_ctas: int = 0, ranges: Optional[torch.Tensor] = None, range_base: int = 0,
-             range_step: int = 0) -> torch.Tensor:
+             range_step: int = 0, split: bool = True) -> torch.Tensor:
     """Launch csa_attn_fwd on the current stream.  All matrices are 2-D ``(rows, heads*64)`` with unit column stride."""
     _require_cuda(q, o)
     ensure_device(q.device)
@@ -328,7 +358,10 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
     a.ca_start, a.ca_step, a.ca_len = ca
     a.cb_start, a.cb_step, a.cb_len = cb
     a.max_ctas = max_ctas
-    a.flags = 0
+    a.flags = 0 if split else CSA_ATTN_NO_SPLIT
+    if split:
+        ws = attn_workspace(q.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     if ranges is not None:
         if ranges.dtype != torch.int32 or not ranges.is_contiguous() or ranges.shape[-1] != 4:
             raise CsaNativeError("ranges must be a contiguous int32 tensor of shape (lists, 4)")
@@ -344,6 +377,13 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
         _check(load().csa_attn_fwd(ctypes.byref(a), _stream_ptr(q)), "csa_attn_fwd")
     LAUNCHES["csa_attn_fwd"] += 1
     return o
+
+
+def last_launch() -> dict:
+    """Work decomposition of this thread's last attention launch (csa_debug_last_launch)."""
+    out = (c_int32 * 4)()
+    _check(load().csa_debug_last_launch(out), "csa_debug_last_launch")
+    return {"ctas": out[0], "whole_units": out[1], "split": out[2], "scheduled": out[3]}
 
 
 def debug_stuck():

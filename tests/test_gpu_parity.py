@@ -286,6 +286,43 @@ def test_attention_strided_inputs():
     assert float(obig[:, :C].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("Fl,N,C,heads,max_ctas", [
+    (4, 1024, 128, 2, 0),      # 64 units on 148 SMs: every unit is split
+    (4, 1024, 1280, 20, 0),    # the 32x32 SDXL layer: 640 units = 4 whole rounds + 48 split units
+    (2, 512, 192, 3, 10),      # 10 CTAs, 24 units: 20 whole + 4 split in two
+    (3, 200, 64, 1, 4),        # ragged tiles, pieces with a single key tile
+])
+def test_attention_tail_split_matches_whole_units(Fl, N, C, heads, max_ctas):
+    """Units of the last, partial round are cut into pieces along the keys and merged by the CTA that delivers the last
+    piece: same result as processing every unit whole (fp32 rounding of the merge aside), launch after launch (the
+    arrival counters are left zero), and within the parity bar of the oracle."""
+    g = torch.Generator().manual_seed(N + heads)
+    T = Fl + 1
+    sample = torch.rand((T * N,), generator=g) < 0.5
+    lists = rp.index_lists(rp.frame_rows(sample, T, Fl))
+    r = sample.to(DEV)
+    s_idx, s_count, ranges = csa_masks.CompactMask(T, Fl, N, sample=r).sample_list(DEV)
+    q, k, v = (torch.randn((2 * Fl * N, C), generator=g).to(torch.bfloat16) for _ in range(3))
+    qd, kd, vd = q.to(DEV), k.to(DEV), v.to(DEV)
+    k_s, v_s, cap = native.gather_kv(kd, vd, Fl * N, 2, s_idx, s_count, Fl * N)
+    kw = dict(heads=heads, n_groups=2, n_frames=Fl, n_q=N, k_a=k_s, v_a=v_s, a_group_rows=cap, ranges=ranges,
+              range_base=0, range_step=1, k_b=kd, v_b=vd, b_group_rows=Fl * N, cb=(0, N, N), max_ctas=max_ctas)
+    whole = native.attn_fwd(qd, torch.empty_like(qd), split=False, **kw)
+    assert native.last_launch()["split"] == 1
+    outs = [native.attn_fwd(qd, torch.full_like(qd, float("nan")), split=True, **kw) for _ in range(3)]
+    assert native.last_launch()["split"] > 1 or (2 * Fl * heads * ((N + 255) // 256)) % (max_ctas or 148) == 0, native.last_launch()
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.isfinite(o.float()).all()
+        assert torch.equal(o, outs[0])                      # deterministic, counters reset between launches
+        assert (o.float() - whole.float()).abs().max().item() <= 4e-3
+    hdr = native.attn_workspace(qd.device)[:4096]
+    assert int(hdr.to(torch.int32).sum()) == 0
+    want = rp.gathered_attention(q.view(2, Fl * N, C), k.view(2, Fl * N, C), v.view(2, Fl * N, C), lists[:Fl],
+                                 heads).reshape(2 * Fl * N, C)
+    _assert_close(outs[0], want, f"tail split F={Fl} N={N} C={C}")
+
+
 # ------------------------------------------------------------------------------------------------ processor vs reference
 def _gpu_attn(z, prefix, C, heads, dtype):
     return attn_from_fixture(z, prefix, C, heads, dtype=dtype, device=DEV)

@@ -52,8 +52,8 @@ def run(F, N, C, heads, sa=0.5, dtype=torch.bfloat16, iters=20):
     vh = v[keys].float().view(-1, heads, 64).transpose(0, 1)[None]
     ref = torch.nn.functional.scaled_dot_product_attention(qh, kh, vh)[0].transpose(0, 1).reshape(N, C)
     err = (o[qs].float() - ref).abs().max().item()
-    print(f"{tag:<22s} F={F} N={N:5d} C={C:4d}: {ms:7.4f} ms {flops / ms * 1e-9:7.1f} TFLOP/s  max-abs {err:.2e}",
-          flush=True)
+    print(f"{tag:<22s} F={F} N={N:5d} C={C:4d}: {ms:7.4f} ms {flops / ms * 1e-9:7.1f} TFLOP/s  max-abs {err:.2e}"
+          f"  {native.last_launch()}", flush=True)
     return ms
 
 
