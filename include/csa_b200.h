@@ -196,6 +196,7 @@ typedef struct csa_attn_args {
 } csa_attn_args_t;
 
 #define CSA_ATTN_NO_SPLIT 1 /* flags: process every unit whole even if a workspace is given */
+#define CSA_ATTN_FORCE_SPLIT(k) (((k) & 0xff) << 8) /* flags, test aid: cut the tail units into exactly k <= 8 pieces */
 
 /*
  * Work decomposition.  A unit = (group, frame, head, pair of 128-query tiles); units are dealt round-robin to one

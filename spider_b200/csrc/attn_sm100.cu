@@ -929,6 +929,8 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
         best_k = k;
       }
     }
+    const int forced = (a->flags >> 8) & 0xff;  // test aid: CSA_ATTN_FORCE_SPLIT(k)
+    if (forced > 0 && forced <= kMaxSplit && static_cast<int64_t>(rem) * forced <= cap_pieces) best_k = forced;
     if (best_k > 1 && rem * 4 <= kWsHeaderBytes) {
       p.split = best_k;
       p.n_whole = p.n_units - rem;

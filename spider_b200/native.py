@@ -322,7 +322,7 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
              list_base: int = -1, list_step: int = 0, g_adjust: int = 0,
              ca: tuple = (0, 0, 0), cb: tuple = (0, 0, 0), scale: Optional[float] = None,
              max_ctas: int = 0, ranges: Optional[torch.Tensor] = None, range_base: int = 0,
-             range_step: int = 0, split: bool = True) -> torch.Tensor:
+             range_step: int = 0, split=True) -> torch.Tensor:
     """Launch csa_attn_fwd on the current stream.  All matrices are 2-D ``(rows, heads*64)`` with unit column stride."""
     _require_cuda(q, o)
     ensure_device(q.device)
@@ -358,7 +358,8 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
     a.ca_start, a.ca_step, a.ca_len = ca
     a.cb_start, a.cb_step, a.cb_len = cb
     a.max_ctas = max_ctas
-    a.flags = 0 if split else CSA_ATTN_NO_SPLIT
+    # split: True = let the library decide, False = whole units only, int k = force k pieces (tests)
+    a.flags = CSA_ATTN_NO_SPLIT if not split else (0 if split is True else (int(split) & 0xff) << 8)
     if split:
         ws = attn_workspace(q.device)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()

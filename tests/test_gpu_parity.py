@@ -286,13 +286,14 @@ def test_attention_strided_inputs():
     assert float(obig[:, :C].abs().sum()) == 0.0
 
 
-@pytest.mark.parametrize("Fl,N,C,heads,max_ctas", [
-    (4, 1024, 128, 2, 0),      # 64 units on 148 SMs: every unit is split
-    (4, 1024, 1280, 20, 0),    # the 32x32 SDXL layer: 640 units = 4 whole rounds + 48 split units
-    (2, 512, 192, 3, 10),      # 10 CTAs, 24 units: 20 whole + 4 split in two
-    (3, 200, 64, 1, 4),        # ragged tiles, pieces with a single key tile
+@pytest.mark.parametrize("Fl,N,C,heads,max_ctas,split", [
+    (4, 1024, 128, 2, 0, True),      # 64 units on 148 SMs: every unit is split
+    (4, 1024, 1280, 20, 0, True),    # the 32x32 SDXL layer: 640 units = 4 whole rounds + 48 split units
+    (2, 512, 192, 3, 10, True),      # 10 CTAs, 24 units: 20 whole + 4 split in two
+    (3, 200, 64, 1, 4, 3),           # ragged tiles, forced 3 pieces of 1-2 key tiles
+    (1, 100, 64, 1, 0, 8),           # 2 units of 1-2 key tiles forced into 8 pieces: most pieces are empty
 ])
-def test_attention_tail_split_matches_whole_units(Fl, N, C, heads, max_ctas):
+def test_attention_tail_split_matches_whole_units(Fl, N, C, heads, max_ctas, split):
     """Units of the last, partial round are cut into pieces along the keys and merged by the CTA that delivers the last
     piece: same result as processing every unit whole (fp32 rounding of the merge aside), launch after launch (the
     arrival counters are left zero), and within the parity bar of the oracle."""
@@ -309,8 +310,8 @@ def test_attention_tail_split_matches_whole_units(Fl, N, C, heads, max_ctas):
               range_base=0, range_step=1, k_b=kd, v_b=vd, b_group_rows=Fl * N, cb=(0, N, N), max_ctas=max_ctas)
     whole = native.attn_fwd(qd, torch.empty_like(qd), split=False, **kw)
     assert native.last_launch()["split"] == 1
-    outs = [native.attn_fwd(qd, torch.full_like(qd, float("nan")), split=True, **kw) for _ in range(3)]
-    assert native.last_launch()["split"] > 1 or (2 * Fl * heads * ((N + 255) // 256)) % (max_ctas or 148) == 0, native.last_launch()
+    outs = [native.attn_fwd(qd, torch.full_like(qd, float("nan")), split=split, **kw) for _ in range(3)]
+    assert native.last_launch()["split"] > 1, native.last_launch()
     torch.cuda.synchronize()
     for o in outs:
         assert torch.isfinite(o.float()).all()
