@@ -316,10 +316,25 @@ def run_b200_arm(args):
             sampler = ClockSampler(local_rank) if rank == 0 else None
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
+            prof = None
+            if args.host_profile and rank == 0:
+                import cProfile
+                prof = cProfile.Profile()
+                prof.enable()
+            t_host0 = time.perf_counter()
             e0.record()
             for _ in range(args.steps):
                 step(record=True)
             e1.record()
+            host_issue_ms = (time.perf_counter() - t_host0) * 1e3   # CPU time to ISSUE the steps (no sync inside)
+            if prof is not None:
+                prof.disable()
+                import io
+                import pstats
+                buf = io.StringIO()
+                pstats.Stats(prof, stream=buf).sort_stats("cumulative").print_stats(45)
+                with open(args.host_profile, "w") as f:
+                    f.write(buf.getvalue())
             barrier()
             ms_total = e0.elapsed_time(e1)
             clocks = sampler.stop() if sampler else None
@@ -372,6 +387,7 @@ def run_b200_arm(args):
             "tflop_per_step": round(flops_total / args.steps / 1e12, 4),
             "gpu_launches": total_launches,
             "launches_by_entry": launches,
+            "host_issue_ms_per_step": round(host_issue_ms / args.steps, 3),
             "clocks": clocks,
             "roofline": {
                 "kernel": "csa_attn_kernel (tcgen05/TMEM flash attention over compacted keys)",
@@ -504,6 +520,7 @@ def main():
     ap.add_argument("--dtype", choices=["bf16", "fp16"], default="bf16")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--host-profile", default="", help="rank 0: cProfile of the timed loop written to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -8,3 +8,6 @@ __version__ = "0.1.0"
 from .install import install, make_processor_class, set_attention_processor, uninstall  # noqa: E402,F401
 from .masks import CompactMask, cal_attn_mask_xl  # noqa: E402,F401
 from .processor import GLOBALS, SpatialAttnProcessor2_0, StoryGlobals  # noqa: E402,F401
+from .lowvram import (CompactIndices, SpatialAttnProcessorLowVram, cal_attn_indice_xl_effcient_memory,  # noqa: E402,F401
+                      install_lowvram, load_single_character_weights, make_lowvram_processor_class,
+                      save_single_character_weights)
