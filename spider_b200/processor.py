@@ -71,6 +71,10 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
     validate_masks = True
     kv_gather = "pre"       # "pre": sampled K/V rows gathered once per layer (csa_gather_kv) and streamed as plain
                             # TMA tiles; "inline": per-frame index lists, TMA gather4 inside the attention kernel
+    batched_read = False    # opt-in: a read call may carry R generated frames (batch 2*R, [uncond R,
+                            # cond R]); each attends bank + itself exactly like a batch-2 call, in ONE launch.  The
+                            # reference generates them one pipe() call at a time (Comic_Generation.py:445-448), so a
+                            # batched call consumes one gate draw where R separate calls consume R.
 
     def __init__(self, hidden_size=None, cross_attention_dim=None, id_length=4, device="cuda", dtype=torch.float16):
         super().__init__()
@@ -185,8 +189,9 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                 raise NotImplementedError("read passes are not sharded: run them on a rank that holds the whole "
                                           "id_bank (spider_b200/dist.py)")
             entry = self.id_bank[cur_step]   # KeyError for a step the write pass never reached (:92)
-            if B != 2:
-                raise ValueError(f"read pass expects batch 2 (uncond, cond), got {B}")
+            if B != 2 and not (self.batched_read and B > 0 and B % 2 == 0):
+                raise ValueError(f"read pass expects batch 2 (uncond, cond), got {B}"
+                                 + ("" if self.batched_read else " (set batched_read=True for 2*R frames)"))
 
         o = torch.empty_like(q)
         branch = "early"
@@ -267,27 +272,27 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
         branch, mask[F*N:], :106-108) + the current frame, per CFG half.  The bank is K/V source A, the current
         projection source B; nothing is concatenated."""
         Fl = self.id_length
+        R = q.shape[0] // (2 * N)          # generated frames in this call (1 unless batched_read)
         kb, vb = entry.kv(attn, device=q.device)
         if kb.shape[0] != 2 * Fl * N or kb.shape[1] != q.shape[1]:
             raise ValueError(f"id_bank entry has K/V of shape {tuple(kb.shape)}, expected {(2 * Fl * N, q.shape[1])}")
         if kb.dtype != q.dtype:
             kb, vb = kb.to(q.dtype), vb.to(q.dtype)
+        # every generated frame r attends the same bank keys + its own block [r*N, (r+1)*N) of the current projection
+        own = dict(k_b=k, v_b=v, b_group_rows=R * N, cb=(0, N, N))
         if cm is None:
-            native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=1, n_q=N,
-                            k_a=kb, v_a=vb, a_group_rows=Fl * N, ca=(0, 0, Fl * N),
-                            k_b=k, v_b=v, b_group_rows=N, cb=(0, 0, N))
+            native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=R, n_q=N,
+                            k_a=kb, v_a=vb, a_group_rows=Fl * N, ca=(0, 0, Fl * N), **own)
         elif self.kv_gather == "pre" and cm.shared_sample:
             s_idx, s_count, ranges = cm.sample_list(q.device)
             k_s, v_s, cap = native.gather_kv(kb, vb, Fl * N, 2, s_idx, s_count, Fl * N)
-            native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=1, n_q=N,
-                            k_a=k_s, v_a=v_s, a_group_rows=cap, ranges=ranges, range_base=Fl, range_step=0,
-                            k_b=k, v_b=v, b_group_rows=N, cb=(0, 0, N))
+            native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=R, n_q=N,
+                            k_a=k_s, v_a=v_s, a_group_rows=cap, ranges=ranges, range_base=Fl, range_step=0, **own)
         else:
             idx, counts = cm.lists(q.device)
-            native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=1, n_q=N,
+            native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=R, n_q=N,
                             k_a=kb, v_a=vb, a_group_rows=Fl * N,
-                            idx=idx, counts=counts, list_base=Fl, list_step=0, g_adjust=-N,
-                            k_b=k, v_b=v, b_group_rows=N, cb=(0, 0, N))
+                            idx=idx, counts=counts, list_base=Fl, list_step=0, g_adjust=-N, **own)
 
 
 def set_bank_store(mode: str, cls=SpatialAttnProcessor2_0) -> None:

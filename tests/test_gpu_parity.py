@@ -540,3 +540,43 @@ def test_sa_one_equals_dense_and_sa_zero_equals_standard():
             native.attn_fwd(q, o_ref, heads=heads, n_groups=2, n_frames=Fl, n_q=N, k_a=k, v_a=v,
                             a_group_rows=Fl * N, ca=(0, 0, Fl * N))
         assert float((o.float() - o_ref.float()).abs().max()) <= 2e-3
+
+
+@pytest.mark.parametrize("cur_step,kv_gather", [(2, "pre"), (25, "pre"), (25, "inline")])
+def test_batched_read_equals_separate_reads(cur_step, kv_gather):
+    """Opt-in batched read pass: R generated frames in one call (batch 2*R, [uncond R, cond R]) give,
+    frame by frame, the output of R reference-style batch-2 calls — early (all bank keys) and consistent branch."""
+    H = W = 512
+    Fl, C, heads, R = 4, 128, 2, 3
+    N = (H // 32) * (W // 32)
+    host = spider_b200.StoryGlobals()
+    host.height, host.width, host.total_count = H, W, 10 ** 9
+    cls = make_processor_class(host)
+    cls.kv_gather = kv_gather
+    torch.manual_seed(5)
+    attn = FakeAttention(C, heads).to(DEV, torch.float16)
+    host.mask1024, host.mask4096 = spider_b200.cal_attn_mask_xl(Fl + 1, Fl, 0.5, 0.5, H, W, device=DEV)
+    proc = cls(id_length=Fl, device=DEV)
+    xw = torch.randn(2 * Fl, N, C, device=DEV, dtype=torch.float16)
+    xr = torch.randn(2, R, N, C, device=DEV, dtype=torch.float16)      # [cfg half][frame]
+    real = random.random
+    random.random = lambda: 0.99
+    try:
+        with torch.no_grad():
+            host.write, host.cur_step = True, cur_step
+            proc(attn, xw)
+            host.write = False
+            singles = []
+            for r in range(R):
+                host.cur_step = cur_step
+                singles.append(proc(attn, xr[:, r].contiguous()))      # (2, N, C)
+            with pytest.raises(ValueError):
+                proc(attn, xr.reshape(2 * R, N, C))                    # batch 2*R is refused unless opted in
+            proc.batched_read = True
+            host.cur_step = cur_step
+            got = proc(attn, xr.reshape(2 * R, N, C)).view(2, R, N, C)
+    finally:
+        random.random = real
+    assert proc._last_branch == ("early" if cur_step < 5 else "consistent")
+    for r in range(R):
+        assert torch.equal(got[:, r], singles[r]), f"frame {r}"
