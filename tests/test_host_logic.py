@@ -151,7 +151,7 @@ def test_launch_geometry_per_branch(recorder):
         host.write, host.cur_step = False, 0
         p(attn, torch.randn(2, N, C))
         kind, kw, shapes, qshape = recorder[-1]
-        assert kw["ca"] == (0, 0, Fl * N) and kw["cb"] == (0, 0, N) and kw["n_frames"] == 1
+        assert kw["ca"] == (0, 0, Fl * N) and kw["cb"] == (0, N, N) and kw["n_frames"] == 1   # frame step N (batched read); single frame here
         assert shapes["k_a"] == (2 * Fl * N, C) and shapes["k_b"] == (2 * N, C)
         host.cur_step = 6   # written above (total_count == 1: every call advances the step)
         random.seed(1)  # 0.134 -> standard, then 0.847 -> consistent
@@ -161,7 +161,7 @@ def test_launch_geometry_per_branch(recorder):
         p(attn, torch.randn(2, N, C))
         kind, kw, shapes, qshape = recorder[-1]
         assert p._last_branch == "consistent"
-        assert (kw["range_base"], kw["range_step"], kw["cb"]) == (Fl, 0, (0, 0, N)) and "list_base" not in kw
+        assert (kw["range_base"], kw["range_step"], kw["cb"]) == (Fl, 0, (0, N, N)) and "list_base" not in kw
         assert shapes["k_b"] == (2 * N, C) and kw["a_group_rows"] == Fl * N + native.CSA_TILE
         host.cur_step = 6
         cls.kv_gather = "inline"
@@ -169,7 +169,7 @@ def test_launch_geometry_per_branch(recorder):
         p(attn, torch.randn(2, N, C))
         cls.kv_gather = "pre"
         kind, kw, shapes, qshape = recorder[-1]
-        assert (kw["list_base"], kw["list_step"], kw["g_adjust"]) == (Fl, 0, -N) and kw["cb"] == (0, 0, N)
+        assert (kw["list_base"], kw["list_step"], kw["g_adjust"]) == (Fl, 0, -N) and kw["cb"] == (0, N, N)
     with pytest.raises(KeyError):
         host.cur_step = 99
         p(attn, torch.randn(2, N, C))
