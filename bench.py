@@ -216,7 +216,11 @@ def workload_config(args, n_gpus: int):
                      f"consistent branch, sa32=sa64={args.sa}"),
         "frames": args.frames, "cfg": 2, "height": args.res, "width": args.res, "sa": args.sa,
         "layers": len(plan), "placement": args.placement, "gate": "forced consistent (cur_step=25)",
-        "parallelism": "single GPU" if n_gpus == 1 else f"(cfg,frame) units sharded over {n_gpus} GPUs",
+        "parallelism": "single GPU" if n_gpus == 1 else (
+            f"(cfg,frame) units sharded over {n_gpus} GPUs"
+            + ("" if n_gpus < 4 else (", sampled K/V rows stored into the peers' buffers over NVLink by the gather "
+                                      "kernel (peer memory, flag-synchronised with the attention kernel)"
+                                      if args.exchange == "p2p" else ", sampled K/V rows all-gathered with NCCL"))),
         "l2": "each layer has its own input latents; per-step working set (inputs + q/k/v/o) far exceeds the 126 MB L2",
     }
 
@@ -261,7 +265,7 @@ def run_b200_arm(args):
     units_local = 2 * Fl
     if world > 1:
         from spider_b200.dist import FrameSharding
-        sharding = FrameSharding(Fl, None, dev)
+        sharding = FrameSharding(Fl, None, dev, exchange=args.exchange)
         units_local = sharding.local_batch
 
     # identical weights / masks on every rank: same seeds (the mask sample must agree across ranks)
@@ -520,6 +524,8 @@ def main():
     ap.add_argument("--dtype", choices=["bf16", "fp16"], default="bf16")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
+                    help="N >= 4: how the sampled K/V rows travel between the GPUs of a CFG half (spider_b200/dist.py)")
     ap.add_argument("--host-profile", default="", help="rank 0: cProfile of the timed loop written to this file")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -17,6 +17,10 @@
  *                            torch.cat of bank and current frames at :92 (two K/V sources are read in place).
  *   csa_gather_rows       <- the row selection implied by the mask when K/V rows have to be materialised
  *                            contiguously (multi-GPU exchange of the sampled rows; bank export).
+ *   csa_peer_scatter_kv,  <- (no reference counterpart: the reference is single-GPU) the per-layer exchange of the
+ *   csa_peer_signal          sampled K/V rows between the GPUs that share one CFG half, fused with their gather:
+ *                            rows are stored straight into every peer's K[S], V[S] buffer over NVLink and the
+ *                            attention kernel of the receiving GPU starts on its local keys meanwhile.
  *   csa_sample_ranges,    <- the observation that the sampled vector of gradio_utils.py:257-261 is ONE list shared by
  *   csa_gather_kv            every frame, CFG half and head: the sampled K/V rows are made contiguous once per layer
  *                            (HBM-bound) and frame f then attends two runs of that buffer plus its own block, so the
@@ -36,7 +40,7 @@
 extern "C" {
 #endif
 
-#define CSA_ABI_VERSION 3
+#define CSA_ABI_VERSION 4
 
 #define CSA_E_BADARG (-1)   /* null pointer, non-positive size, misaligned pointer/stride */
 #define CSA_E_SHAPE (-2)    /* unsupported geometry (head_dim != 64, row stride not 16-byte aligned, ...) */
@@ -48,6 +52,7 @@ extern "C" {
 
 #define CSA_HEAD_DIM 64
 #define CSA_TILE 128 /* keys per tile; index-list rows must be padded to a multiple of this */
+#define CSA_MAX_PEERS 8 /* GPUs that can share one K[S], V[S] buffer over peer memory (one CFG half of a 16-GPU job) */
 
 int csa_abi_version(void);
 const char* csa_last_error(void);
@@ -193,9 +198,20 @@ typedef struct csa_attn_args {
    * zero again); one workspace must not be shared by launches that may run concurrently.  NULL = never split. */
   void* workspace;
   int64_t workspace_bytes;
+
+  /* Multi-GPU (optional, NULL = everything is local): rows [ready_bounds[r], ready_bounds[r+1]) of every group of
+   * k_a / v_a are written into this GPU's memory by peer rank r (csa_peer_scatter_kv on that GPU); the kernel
+   * reads them only once ready[r] >= ready_epoch (device uint32[ready_n], polled with ld.acquire.sys).  Contiguous
+   * runs of A only (ranges / ca_*), not index lists.  Combine with CSA_ATTN_B_FIRST so that the local B segment
+   * is worked on while the peers' rows are in flight. */
+  const uint32_t* ready;
+  uint32_t ready_epoch;
+  int32_t ready_n;
+  int32_t ready_bounds[CSA_MAX_PEERS + 1];
 } csa_attn_args_t;
 
 #define CSA_ATTN_NO_SPLIT 1 /* flags: process every unit whole even if a workspace is given */
+#define CSA_ATTN_B_FIRST 2  /* flags: key order of a unit = contiguous B segment first, then A (default: A, then B) */
 #define CSA_ATTN_FORCE_SPLIT(k) (((k) & 0xff) << 8) /* flags, test aid: cut the tail units into exactly k <= 8 pieces */
 
 /*
@@ -213,6 +229,62 @@ int csa_debug_last_launch(int32_t* out4_host);
 
 /* Bytes of workspace that let csa_attn_fwd split on `ctas` CTAs (0 = one per SM of the current device). */
 int64_t csa_attn_workspace_bytes(int32_t ctas);
+
+/*
+ * Multi-GPU exchange of the sampled K/V rows, fused with their gather (replaces gather -> NCCL all-gather ->
+ * compaction).  The reference is single-GPU; this is the scale-out of the write pass (Comic_Generation.py:148: the
+ * F frames of one CFG half form one key sequence, so with the frames sharded over `n_peers` GPUs every GPU needs
+ * the sampled rows of all of them).  Every GPU of the group owns a buffer pair K[S], V[S] laid out in the order of
+ * the sampled list S; rank `self` holds the rows S[dst_row0 .. dst_row0 + count) (those of its own frames) and
+ * this call stores them DIRECTLY into the buffers of all `n_peers` GPUs (peer pointers over NVLink; [self] is the
+ * local buffer):
+ *     k_dst[r][(dst_row0 + i) * dst_ld_bytes ...] = k[idx[i] * ld_bytes ...]   for every r, i < count    (same for v)
+ * then publishes `epoch` to ready[r][self] on every GPU r (st.release.sys after a system-scope fence), which is what
+ * csa_attn_fwd(ready = ...) on GPU r waits for.  Before writing, the kernel waits until done[r] >= done_epoch for
+ * every r != self: GPU r has finished the attention launch that last read the buffers being overwritten
+ * (csa_peer_signal).  `counter` is a zero-initialised local device uint32 (left zero again).
+ * Epochs are monotonically increasing uint32 (start at 1, flags zero-initialised).  HBM/NVLink-bound.
+ */
+typedef struct csa_peer_scatter_args {
+  uint32_t struct_size; /* sizeof(csa_peer_scatter_args_t), checked */
+  int32_t n_peers;      /* 1 .. CSA_MAX_PEERS */
+  int32_t self;         /* index of this GPU among them */
+  int32_t row_bytes;    /* multiple of 16 */
+  const void* k;
+  const void* v;
+  int64_t ld_bytes;
+  const int32_t* idx; /* device int32[count]: rows of k / v that are sampled, ascending */
+  int32_t count;
+  int32_t dst_row0;
+  void* k_dst[CSA_MAX_PEERS];
+  void* v_dst[CSA_MAX_PEERS];
+  int64_t dst_ld_bytes;
+  uint32_t* ready[CSA_MAX_PEERS]; /* ready[r]: GPU r's arrival flags, uint32[n_peers] */
+  uint32_t epoch;
+  uint32_t done_epoch;
+  const uint32_t* done; /* LOCAL uint32[n_peers], written by the peers */
+  uint32_t* counter;    /* LOCAL, zero */
+} csa_peer_scatter_args_t;
+
+int csa_peer_scatter_kv(const csa_peer_scatter_args_t* args, void* stream);
+
+/* done[r][self] = epoch on every GPU r != self (st.release.sys): everything this GPU enqueued on `stream` before
+ * this call — in particular the attention launch that read the exchange buffers of `epoch` — has completed. */
+int csa_peer_signal(uint32_t* const* done, int32_t n_peers, int32_t self, uint32_t epoch, void* stream);
+
+/* Enable loads/stores from the current device to memory of `peer_device` (cudaDeviceEnablePeerAccess; already
+ * enabled is not an error).  Host-side setup helper. */
+int csa_enable_peer_access(int32_t peer_device);
+
+/*
+ * Host-side setup helpers for the peer exchange (one process per GPU): export a device allocation of this process
+ * (handle64_out: 64 bytes = cudaIpcMemHandle_t of the allocation that contains `ptr`, *offset_out = ptr - its base) and
+ * map another process's allocation into the CURRENT device's address space with peer access enabled lazily
+ * (*base_out = base of the mapped allocation; close it with csa_ipc_close before the owner frees the memory).
+ */
+int csa_ipc_export(const void* ptr, void* handle64_out, int64_t* offset_out);
+int csa_ipc_open(const void* handle64, void** base_out);
+int csa_ipc_close(void* base);
 
 #ifdef __cplusplus
 }

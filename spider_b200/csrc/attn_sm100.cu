@@ -134,6 +134,13 @@ struct AttnKernelParams {
   int32_t n_whole, split, n_sched;
   float* ws;           // split pieces: [piece][256 rows][64] O, then [256] m, then [256] l
   uint32_t* ws_count;  // one arrival counter per split unit (zero between launches)
+  // Multi-GPU: rows [ready_bounds[r], ready_bounds[r+1]) of every group of A are delivered by peer rank r straight
+  // into this GPU's memory (csa_peer_scatter_kv); they may be read once ready[r] >= ready_epoch.
+  const uint32_t* ready;
+  uint32_t ready_epoch;
+  int32_t ready_n;
+  int32_t ready_bounds[CSA_MAX_PEERS + 1];
+  int32_t b_first;  // key order of a unit: contiguous B segment first, then the runs of A
 };
 
 constexpr int kPieceFloats = 2 * kBM * (kHD + 2);  // partial of one piece of a Q-tile pair
@@ -149,7 +156,7 @@ struct Unit {
   const int32_t* gidx;
   int a_base;  // row offset of this group in A
   int seg_row[kMaxSeg], seg_len[kMaxSeg], seg_tiles[kMaxSeg];
-  int seg_b;   // index of the first segment that lives in source B (segments before it are in A)
+  int seg_in_b;  // bit i set: segment i lives in source B (else in A)
   int tg, total;
   int t0, nt;     // this CTA's share of the unit's key tiles: [t0, t0 + nt) (the whole unit unless split)
   int piece;      // index of the partial in the workspace, or -1 for a whole unit
@@ -184,21 +191,30 @@ __device__ __forceinline__ Unit decode_unit(const AttnKernelParams& p, int sched
     w.gidx = p.idx + static_cast<int64_t>(list) * p.idx_stride;
   }
   w.a_base = w.g * p.a_group_rows;
+  int a_row[2], a_len[2];
   if (p.ranges != nullptr) {
     const int4 rg = __ldg(reinterpret_cast<const int4*>(p.ranges) + (p.range_base + w.f * p.range_step));
-    w.seg_row[0] = w.a_base + rg.x;
-    w.seg_len[0] = rg.y > 0 ? rg.y : 0;
-    w.seg_row[1] = w.a_base + rg.z;
-    w.seg_len[1] = rg.w > 0 ? rg.w : 0;
+    a_row[0] = w.a_base + rg.x;
+    a_len[0] = rg.y > 0 ? rg.y : 0;
+    a_row[1] = w.a_base + rg.z;
+    a_len[1] = rg.w > 0 ? rg.w : 0;
   } else {
-    w.seg_row[0] = w.a_base + p.ca_start + w.f * p.ca_step;
-    w.seg_len[0] = p.ca_len;
-    w.seg_row[1] = 0;
-    w.seg_len[1] = 0;
+    a_row[0] = w.a_base + p.ca_start + w.f * p.ca_step;
+    a_len[0] = p.ca_len;
+    a_row[1] = 0;
+    a_len[1] = 0;
   }
-  w.seg_b = 2;
-  w.seg_row[2] = w.g * p.b_group_rows + p.cb_start + w.f * p.cb_step;
-  w.seg_len[2] = p.cb_len;
+  const int b_row = w.g * p.b_group_rows + p.cb_start + w.f * p.cb_step;
+  // segment order = key order of the unit: A run 1, A run 2, B — or B first (multi-GPU: the frame's own block is
+  // local, so its tiles are worked on while the sampled rows of the other GPUs are still in flight)
+  const bool bf = p.b_first != 0;
+  w.seg_row[0] = bf ? b_row : a_row[0];
+  w.seg_len[0] = bf ? p.cb_len : a_len[0];
+  w.seg_row[1] = bf ? a_row[0] : a_row[1];
+  w.seg_len[1] = bf ? a_len[0] : a_len[1];
+  w.seg_row[2] = bf ? a_row[1] : b_row;
+  w.seg_len[2] = bf ? a_len[1] : p.cb_len;
+  w.seg_in_b = bf ? 1 : 4;
   w.tg = (w.ng + kBN - 1) / kBN;
   w.total = w.tg;
 #pragma unroll
@@ -282,6 +298,7 @@ __device__ __forceinline__ int tile_valid(const Unit& w, int t) {
 __device__ __forceinline__ void producer_warp(const AttnKernelParams& p, const uint32_t sb, const int lane) {
   int ks = 0, vs = 0;
   uint32_t kph = 0, vph = 0, qph = 0;
+  uint32_t confirmed = 0;  // peers whose rows of A are known to have landed (multi-GPU)
   for (int u = blockIdx.x; u < p.n_sched; u += gridDim.x) {
     const Unit w = decode_unit(p, u);
     if (w.nt == 0) continue;
@@ -335,7 +352,19 @@ __device__ __forceinline__ void producer_warp(const AttnKernelParams& p, const u
         locate_tile(w, t, seg, local);
         const int srow = seg == 0 ? w.seg_row[0] : (seg == 1 ? w.seg_row[1] : w.seg_row[2]);
         row0 = srow + local * kBN;
-        const bool in_b = seg >= w.seg_b;
+        const bool in_b = (w.seg_in_b >> seg) & 1;
+        if (!in_b && p.ready != nullptr) {
+          // rows [lo, hi) of this group's A are about to be read: wait for the peers that deliver them
+          const int slen = seg == 0 ? w.seg_len[0] : (seg == 1 ? w.seg_len[1] : w.seg_len[2]);
+          const int lo = row0 - w.a_base;
+          const int hi = min(lo + kBN, srow - w.a_base + slen);
+          for (int r = 0; r < p.ready_n; ++r) {
+            if (((confirmed >> r) & 1u) == 0u && p.ready_bounds[r] < hi && p.ready_bounds[r + 1] > lo) {
+              flag_wait_ge(p.ready + r, p.ready_epoch, 0x130 + r, p.dbg);
+              confirmed |= 1u << r;
+            }
+          }
+        }
         mk = in_b ? &p.tm_kb : &p.tm_ka;
         mv = in_b ? &p.tm_vb : &p.tm_va;
       }
@@ -892,6 +921,20 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
   p.range_base = a->range_base;
   p.range_step = a->range_step;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.b_first = (a->flags & CSA_ATTN_B_FIRST) ? 1 : 0;
+  p.ready = nullptr;
+  if (a->ready != nullptr) {
+    if (a->ready_n <= 0 || a->ready_n > CSA_MAX_PEERS || (reinterpret_cast<uintptr_t>(a->ready) & 3))
+      return set_error(CSA_E_BADARG, "csa_attn_fwd: ready_n must be in [1, %d] and ready 4-byte aligned", CSA_MAX_PEERS);
+    if (use_g) return set_error(CSA_E_BADARG, "csa_attn_fwd: arrival flags cover contiguous runs of A only, not index lists");
+    for (int r = 0; r < a->ready_n; ++r)
+      if (a->ready_bounds[r] > a->ready_bounds[r + 1])
+        return set_error(CSA_E_BADARG, "csa_attn_fwd: ready_bounds must be non-decreasing");
+    p.ready = a->ready;
+    p.ready_epoch = a->ready_epoch;
+    p.ready_n = a->ready_n;
+    for (int r = 0; r <= a->ready_n; ++r) p.ready_bounds[r] = a->ready_bounds[r];
+  }
   p.dbg = debug_record_devptr();
 
   int dev = 0;

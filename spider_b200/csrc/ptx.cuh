@@ -219,6 +219,39 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+// ----------------------------------------------------------------------------------------------- peer flags
+// Flags in global memory written by OTHER GPUs over NVLink (st.release.sys after their data stores) and polled
+// here; the data is then read through TMA (async proxy), hence the proxy fence after the acquire.
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+#ifndef CSA_FLAG_WATCHDOG_POLLS
+#define CSA_FLAG_WATCHDOG_POLLS (1u << 25)
+#endif
+__device__ __forceinline__ void flag_wait_ge(const uint32_t* flag, uint32_t epoch, uint32_t tag = 0,
+                                             volatile uint32_t* dbg = nullptr) {
+  uint32_t polls = 0;
+  while (ld_acquire_sys(flag) < epoch) {
+    __nanosleep(100);
+    if (++polls == CSA_FLAG_WATCHDOG_POLLS) {
+      if (dbg != nullptr && dbg[0] == 0u) {
+        dbg[1] = blockIdx.x;
+        dbg[2] = threadIdx.x;
+        dbg[3] = epoch;
+        dbg[0] = tag | 0x80000000u;
+      }
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------------------- packed fp32 math
 // Blackwell issues 2-wide fp32 FMA/ADD (FFMA2 / FADD2) and a 3-input max (FMNMX3): they halve the FMA-/ALU-pipe
 // instruction count of the softmax inner loop, which competes with the MUFU for issue slots.

@@ -7,11 +7,16 @@ half frame f attends ``S u block_f`` where S — the sampled key positions — i
 
   * ranks ``[0, G/2)`` hold the unconditional half, ranks ``[G/2, G)`` the conditional half; inside a half the F
     identity frames are split into contiguous runs of ``F / (G/2)`` frames per rank;
-  * every layer runs on the local frames only; in the consistent branch each rank gathers the sampled rows of ITS
-    frames from its K/V projections (``csa_gather_rows``, HBM-bound), the slabs are all-gathered inside the half over
-    NVLink (NCCL; nothing crosses between the halves), compacted into the same ``K[S], V[S]`` buffers the single-GPU
-    path builds (``csa_gather_kv``), and the local frames attend ``two runs of that buffer + their own block`` with
-    the unchanged attention kernel;
+  * every layer runs on the local frames only; in the consistent branch the sampled rows of the frames of one half
+    are exchanged inside that half over NVLink (nothing crosses between the halves) into the same S-ordered
+    ``K[S], V[S]`` buffers the single-GPU path builds, and the local frames attend ``two runs of that buffer + their
+    own block`` with the same attention kernel.  Two exchange paths:
+      - ``exchange="p2p"`` (default): ONE kernel per rank gathers its sampled rows and stores them straight into
+        every peer's buffer over peer memory (``csa_peer_scatter_kv``), then raises a flag there; the receiver's
+        attention kernel starts with each frame's own (local) block and waits for a peer's flag only when it reaches
+        that peer's rows — the transfer is hidden behind the attention of the local keys (``PeerExchange``);
+      - ``exchange="nccl"``: gather (``csa_gather_rows``) -> NCCL all-gather -> compaction (``csa_gather_kv``),
+        kept as the library baseline the fused path is measured against;
   * G == 2 needs no exchange at all (one half per GPU).
 
 All sizes are known on every rank because S is global: the sample vector is broadcast from rank 0 whenever it is
@@ -30,6 +35,101 @@ import torch
 import torch.distributed as dist
 
 from . import native
+
+
+def _export_tensor(t: torch.Tensor):
+    """Picklable handle of a tensor's memory for the other ranks of this box.  Device memory: a CUDA IPC handle of
+    the allocation (``csa_ipc_export``).  Host memory (the gloo tests): torch's shared-memory reduction."""
+    if t.is_cuda:
+        return ("cuda", native.ipc_export(t))
+    from multiprocessing.reduction import ForkingPickler
+
+    import torch.multiprocessing.reductions  # noqa: F401  (registers the tensor / storage reducers)
+    return ("host", bytes(ForkingPickler.dumps(t)))
+
+
+def _import_tensor(handle, device) -> torch.Tensor:
+    """Map a peer's buffer; nothing is copied.  Device memory is opened with THIS rank's device current, so that the
+    mapping — and the peer access CUDA enables lazily with it — belongs to the device whose kernels store through it
+    (a mapping opened under the exporter's device index, as torch's own CUDA IPC rebuild does, faults when written
+    from another device: tools/ipc_probe.py).  Returned as a flat uint8 tensor."""
+    kind, h = handle
+    if kind == "cuda":
+        return native.ipc_import(h, device)
+    import pickle
+    return pickle.loads(h).view(torch.uint8).view(-1)
+
+
+class PeerExchange:
+    """Symmetric exchange buffers of one CFG half: on every rank two slots of (K[S], V[S]) byte buffers plus arrival
+    (``ready``) and release (``done``) flags, each mapped into every peer (CUDA IPC + P2P access).  Layer calls are
+    numbered by a monotonically increasing epoch (all ranks make the same calls in the same order); epoch e uses
+    slot e % 2, so a rank may run one layer ahead of the slowest peer before ``csa_peer_scatter_kv`` has to wait
+    for that peer's ``done`` flag."""
+
+    SLOTS = 2
+
+    def __init__(self, sh: "FrameSharding", device):
+        self.sh = sh
+        self.device = torch.device(device)
+        self.cap_bytes = 0
+        self.epoch = 0
+        self.bufs = None      # per rank: uint8 tensor [SLOTS * 2 * cap_bytes]
+        self.flags = None     # per rank: int32 tensor [3, CSA_MAX_PEERS]: ready, done, {counter, ...}
+        self._keep = None
+        self.allocations = 0
+
+    def ensure(self, need_bytes: int) -> None:
+        """Collective over the half group: (re)allocate and re-map the buffers when a layer needs more room."""
+        if need_bytes <= self.cap_bytes:
+            return
+        sh = self.sh
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        dist.barrier(group=sh.half_group)          # nobody is still reading or writing the old buffers
+        cap = (need_bytes + 4095) // 4096 * 4096
+        local = torch.zeros(self.SLOTS * 2 * cap, dtype=torch.uint8, device=self.device)
+        flags = torch.zeros(3 * native.CSA_MAX_PEERS * 4, dtype=torch.uint8, device=self.device)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)    # the zeros are in memory before anybody maps the buffers
+        handles = [None] * sh.gc
+        dist.all_gather_object(handles, (_export_tensor(local), _export_tensor(flags), self.epoch),
+                               group=sh.half_group)
+        me = sh.rank_in_half
+        self._keep = (local, flags)                # the peers' mappings alias these allocations
+        self.bufs, self.flags = [], []
+        for r, (hb, hf, ep) in enumerate(handles):
+            if ep != self.epoch:
+                raise RuntimeError("ranks diverged: peer exchange epochs differ (not every rank made the same calls)")
+            b, f = (local, flags) if r == me else (_import_tensor(hb, self.device), _import_tensor(hf, self.device))
+            self.bufs.append(b)
+            self.flags.append(f.view(torch.int32).view(3, native.CSA_MAX_PEERS))
+        self.cap_bytes = cap
+        self.epoch = 0    # fresh flags: epochs restart
+        self.allocations += 1
+        dist.barrier(group=sh.half_group)          # every rank has mapped every buffer before the first store
+
+    def views(self, slot: int, rows: int, cols: int, dtype):
+        """Per rank the (K[S], V[S]) views [rows, cols] of ``slot``."""
+        nbytes = rows * cols * torch.empty((), dtype=dtype).element_size()
+        if nbytes > self.cap_bytes:
+            raise ValueError("PeerExchange.ensure() was not called for this layer size")
+        ks, vs = [], []
+        for b in self.bufs:
+            k0 = (slot * 2) * self.cap_bytes
+            v0 = (slot * 2 + 1) * self.cap_bytes
+            ks.append(b[k0:k0 + nbytes].view(dtype).view(rows, cols))
+            vs.append(b[v0:v0 + nbytes].view(dtype).view(rows, cols))
+        return ks, vs
+
+    def ready(self):
+        return [f[0] for f in self.flags]
+
+    def done(self):
+        return [f[1] for f in self.flags]
+
+    def counter(self):
+        return self.flags[self.sh.rank_in_half][2]
 
 
 class ShardPlan:
@@ -55,12 +155,18 @@ class ShardPlan:
         parts = [torch.arange(c, dtype=torch.int32, device=device) + 2 * r * self.pad
                  for r, c in enumerate(self.counts)]
         self.slab_map = torch.cat(parts) if parts else torch.zeros((0,), dtype=torch.int32, device=device)
+        # rows [bounds[r], bounds[r+1]) of the S-ordered buffer are the sampled rows of rank r's frames
+        self.bounds = [self.lo[r] for r in range(sh.gc)] + [self.hi[sh.gc - 1]]
 
 
 class FrameSharding:
     """Static assignment of (CFG half, frame) units to the ranks of ``group`` (default: the world)."""
 
-    def __init__(self, id_length: int, group=None, device: Optional[torch.device] = None):
+    def __init__(self, id_length: int, group=None, device: Optional[torch.device] = None, exchange: str = "p2p"):
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' (fused gather + peer-memory scatter) or 'nccl' (all-gather)")
+        self.exchange = exchange
+        self.peers: Optional[PeerExchange] = None
         if not dist.is_initialized():
             raise RuntimeError("FrameSharding needs an initialised torch.distributed process group")
         self.group = group
@@ -130,6 +236,8 @@ class FrameSharding:
             raise ValueError("sharded consistent attention needs masks whose rows share one sample vector")
         C = q.shape[1]
         pl = self.plan(cm, q.device)
+        if self.gc > 1 and self.exchange == "p2p":
+            return self._attn_write_p2p(q, k, v, o, N, heads, pl, Fl)
         if self.gc == 1:
             # one CFG half per GPU: everything is local, same as the single-GPU path with one group
             k_s, v_s, cap = native.gather_kv(k, v, Fl * N, 1, pl.s_idx, pl.s_count, Fl * N)
@@ -148,4 +256,30 @@ class FrameSharding:
         native.attn_fwd(q, o, heads=heads, n_groups=1, n_frames=fr, n_q=N,
                         k_a=k_s, v_a=v_s, a_group_rows=cap, ranges=pl.ranges, range_base=self.f0, range_step=1,
                         k_b=k, v_b=v, b_group_rows=fr * N, cb=(0, N, N))
+        return o
+
+    def _attn_write_p2p(self, q, k, v, o, N, heads, pl: ShardPlan, Fl):
+        """Fused exchange: this rank's sampled rows go straight into every peer's S-ordered K[S], V[S] buffer
+        (one kernel), the attention launch starts on the frames' own blocks and picks up each peer's rows when
+        their flag is up, and a last tiny kernel tells the peers that the buffers of this epoch were read."""
+        C = q.shape[1]
+        fr = self.frames_local
+        me = self.rank_in_half
+        if self.peers is None:
+            self.peers = PeerExchange(self, q.device)
+        ex = self.peers
+        rows = Fl * N + native.CSA_TILE            # S has at most F*N rows; a ragged last tile may overhang
+        ex.ensure(rows * C * k.element_size())
+        ex.epoch += 1
+        epoch = ex.epoch
+        ks, vs = ex.views(epoch % ex.SLOTS, rows, C, k.dtype)
+        # peers last read this slot in epoch - SLOTS
+        native.peer_scatter_kv(k, v, pl.local_idx, pl.count_me, pl.lo[me], ks, vs, ex.ready(), me, epoch,
+                               ex.done()[me], max(0, epoch - ex.SLOTS), ex.counter())
+        self.bytes_exchanged += (self.gc - 1) * 2 * pl.count_me * C * k.element_size()
+        native.attn_fwd(q, o, heads=heads, n_groups=1, n_frames=fr, n_q=N,
+                        k_a=ks[me], v_a=vs[me], a_group_rows=rows, ranges=pl.ranges, range_base=self.f0,
+                        range_step=1, k_b=k, v_b=v, b_group_rows=fr * N, cb=(0, N, N),
+                        b_first=True, ready=ex.ready()[me], ready_epoch=epoch, ready_bounds=pl.bounds)
+        native.peer_signal(ex.done(), me, epoch, q)
         return o

@@ -19,11 +19,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CSA_B200_LIB: developer knob to load an experimental build of the same ABI (kernel tuning sweeps); default in-tree
 LIB_PATH = os.environ.get("CSA_B200_LIB") or os.path.join(_HERE, "libcsa_b200.so")
 
-CSA_ABI_VERSION = 3
+CSA_ABI_VERSION = 4
 CSA_DTYPE_F16 = 0
 CSA_DTYPE_BF16 = 1
 CSA_TILE = 128
 CSA_HEAD_DIM = 64
+CSA_MAX_PEERS = 8
 
 # every symbol include/csa_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -40,6 +41,12 @@ EXPORTED_SYMBOLS = (
     "csa_attn_fwd",
     "csa_attn_workspace_bytes",
     "csa_debug_last_launch",
+    "csa_peer_scatter_kv",
+    "csa_peer_signal",
+    "csa_enable_peer_access",
+    "csa_ipc_export",
+    "csa_ipc_open",
+    "csa_ipc_close",
 )
 
 
@@ -94,10 +101,40 @@ class CsaAttnArgs(ctypes.Structure):
         ("range_step", c_int32),
         ("workspace", c_void_p),
         ("workspace_bytes", c_int64),
+        ("ready", c_void_p),
+        ("ready_epoch", c_uint32),
+        ("ready_n", c_int32),
+        ("ready_bounds", c_int32 * (CSA_MAX_PEERS + 1)),
+    ]
+
+
+class CsaPeerScatterArgs(ctypes.Structure):
+    """Mirror of ``csa_peer_scatter_args_t`` (include/csa_b200.h)."""
+
+    _fields_ = [
+        ("struct_size", c_uint32),
+        ("n_peers", c_int32),
+        ("self_", c_int32),
+        ("row_bytes", c_int32),
+        ("k", c_void_p),
+        ("v", c_void_p),
+        ("ld_bytes", c_int64),
+        ("idx", c_void_p),
+        ("count", c_int32),
+        ("dst_row0", c_int32),
+        ("k_dst", c_void_p * CSA_MAX_PEERS),
+        ("v_dst", c_void_p * CSA_MAX_PEERS),
+        ("dst_ld_bytes", c_int64),
+        ("ready", c_void_p * CSA_MAX_PEERS),
+        ("epoch", c_uint32),
+        ("done_epoch", c_uint32),
+        ("done", c_void_p),
+        ("counter", c_void_p),
     ]
 
 
 CSA_ATTN_NO_SPLIT = 1
+CSA_ATTN_B_FIRST = 2
 
 
 _lib: Optional[ctypes.CDLL] = None
@@ -105,7 +142,7 @@ _lib: Optional[ctypes.CDLL] = None
 # Launch accounting (how many of OUR kernels were launched, by entry point) and optional CUDA-event timing of the
 # attention launches on the launching stream; both are read by bench.py.
 LAUNCHES = {"csa_attn_fwd": 0, "csa_compact_rows": 0, "csa_validate_mask": 0, "csa_gather_rows": 0,
-            "csa_sample_ranges": 0, "csa_gather_kv": 0}
+            "csa_sample_ranges": 0, "csa_gather_kv": 0, "csa_peer_scatter_kv": 0, "csa_peer_signal": 0}
 ATTN_EVENTS: Optional[list] = None   # when a list: (start_event, end_event, n_groups, n_frames, n_q, heads) appended
 
 
@@ -158,6 +195,18 @@ def load() -> ctypes.CDLL:
     lib.csa_debug_last_launch.argtypes = [POINTER(c_int32)]
     lib.csa_attn_workspace_bytes.restype = c_int64
     lib.csa_attn_workspace_bytes.argtypes = [c_int32]
+    lib.csa_peer_scatter_kv.restype = c_int32
+    lib.csa_peer_scatter_kv.argtypes = [POINTER(CsaPeerScatterArgs), c_void_p]
+    lib.csa_peer_signal.restype = c_int32
+    lib.csa_peer_signal.argtypes = [POINTER(c_void_p), c_int32, c_int32, c_uint32, c_void_p]
+    lib.csa_enable_peer_access.restype = c_int32
+    lib.csa_enable_peer_access.argtypes = [c_int32]
+    lib.csa_ipc_export.restype = c_int32
+    lib.csa_ipc_export.argtypes = [c_void_p, c_void_p, POINTER(c_int64)]
+    lib.csa_ipc_open.restype = c_int32
+    lib.csa_ipc_open.argtypes = [c_void_p, POINTER(c_void_p)]
+    lib.csa_ipc_close.restype = c_int32
+    lib.csa_ipc_close.argtypes = [c_void_p]
 
     v = lib.csa_abi_version()
     if v != CSA_ABI_VERSION:
@@ -336,7 +385,8 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
              list_base: int = -1, list_step: int = 0, g_adjust: int = 0,
              ca: tuple = (0, 0, 0), cb: tuple = (0, 0, 0), scale: Optional[float] = None,
              max_ctas: int = 0, ranges: Optional[torch.Tensor] = None, range_base: int = 0,
-             range_step: int = 0, split=True) -> torch.Tensor:
+             range_step: int = 0, split=True, b_first: bool = False, ready: Optional[torch.Tensor] = None,
+             ready_epoch: int = 0, ready_bounds=None) -> torch.Tensor:
     """Launch csa_attn_fwd on the current stream.  All matrices are 2-D ``(rows, heads*64)`` with unit column stride."""
     _require_cuda(q, o)
     ensure_device(q.device)
@@ -374,6 +424,16 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
     a.max_ctas = max_ctas
     # split: True = let the library decide, False = whole units only, int k = force k pieces (tests)
     a.flags = CSA_ATTN_NO_SPLIT if not split else (0 if split is True else (int(split) & 0xff) << 8)
+    if b_first:
+        a.flags |= CSA_ATTN_B_FIRST
+    if ready is not None:
+        # rows [ready_bounds[r], ready_bounds[r+1]) of A are delivered by peer r (peer_scatter_kv on that GPU)
+        n = len(ready_bounds) - 1
+        if ready.dtype != torch.int32 or not ready.is_contiguous() or ready.numel() < n or not 1 <= n <= CSA_MAX_PEERS:
+            raise CsaNativeError("ready must be a contiguous int32 tensor with one flag per peer (<= 8 peers)")
+        a.ready, a.ready_epoch, a.ready_n = ready.data_ptr(), ready_epoch, n
+        for i, b in enumerate(ready_bounds):
+            a.ready_bounds[i] = b
     stream = _stream_ptr(q)
     if split:
         ws = attn_workspace(q.device, stream)
@@ -393,6 +453,91 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
         _check(load().csa_attn_fwd(ctypes.byref(a), stream), "csa_attn_fwd")
     LAUNCHES["csa_attn_fwd"] += 1
     return o
+
+
+def peer_scatter_kv(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, count: int, dst_row0: int, k_dst, v_dst,
+                    ready, self_index: int, epoch: int, done: torch.Tensor, done_epoch: int,
+                    counter: torch.Tensor) -> None:
+    """Store this GPU's sampled K/V rows into the S-ordered buffers of every GPU of the group and raise its arrival
+    flag there (see csa_peer_scatter_kv).  ``k_dst / v_dst / ready`` are lists of tensors, one per GPU (peer memory;
+    entry ``self_index`` is local); ``done`` and ``counter`` are local."""
+    _require_cuda(k, v, done, counter)
+    ensure_device(k.device)
+    n = len(k_dst)
+    if not (1 <= n <= CSA_MAX_PEERS) or len(v_dst) != n or len(ready) != n:
+        raise CsaNativeError(f"peer_scatter_kv: 1..{CSA_MAX_PEERS} peers, one K, V and flag buffer each")
+    if k.dim() != 2 or k.stride(1) != 1 or v.shape != k.shape or v.stride(0) != k.stride(0):
+        raise CsaNativeError("peer_scatter_kv expects 2-D k/v of equal shape and row stride, unit column stride")
+    es = k.element_size()
+    a = CsaPeerScatterArgs()
+    a.struct_size = ctypes.sizeof(CsaPeerScatterArgs)
+    a.n_peers, a.self_, a.row_bytes = n, self_index, k.shape[1] * es
+    a.k, a.v, a.ld_bytes = k.data_ptr(), v.data_ptr(), k.stride(0) * es
+    a.idx, a.count, a.dst_row0 = (idx.data_ptr() if count > 0 else None), count, dst_row0
+    ld = None
+    for r in range(n):
+        kd, vd = k_dst[r], v_dst[r]
+        if kd.dim() != 2 or kd.stride(1) != 1 or kd.shape[1] != k.shape[1] or kd.dtype != k.dtype or \
+                vd.shape != kd.shape or vd.stride(0) != kd.stride(0) or (ld is not None and kd.stride(0) != ld):
+            raise CsaNativeError("peer_scatter_kv: destination buffers must be 2-D, of k's width/dtype and one stride")
+        if dst_row0 + count > kd.shape[0]:
+            raise CsaNativeError(f"peer_scatter_kv: rows [{dst_row0}, {dst_row0 + count}) exceed the buffer "
+                                 f"({kd.shape[0]} rows)")
+        ld = kd.stride(0)
+        a.k_dst[r], a.v_dst[r], a.ready[r] = kd.data_ptr(), vd.data_ptr(), ready[r].data_ptr()
+    a.dst_ld_bytes = ld * es
+    a.epoch, a.done_epoch = epoch, done_epoch
+    a.done, a.counter = done.data_ptr(), counter.data_ptr()
+    _check(load().csa_peer_scatter_kv(ctypes.byref(a), _stream_ptr(k)), "csa_peer_scatter_kv")
+    LAUNCHES["csa_peer_scatter_kv"] += 1
+
+
+def peer_signal(done, self_index: int, epoch: int, like: torch.Tensor) -> None:
+    """done[r][self_index] = epoch on every other GPU r, ordered after everything enqueued so far on the current
+    stream of ``like``'s device (see csa_peer_signal)."""
+    n = len(done)
+    arr = (c_void_p * n)(*[t.data_ptr() for t in done])
+    _check(load().csa_peer_signal(arr, n, self_index, epoch, _stream_ptr(like)), "csa_peer_signal")
+    LAUNCHES["csa_peer_signal"] += 1
+
+
+def enable_peer_access(peer_device: int) -> None:
+    _check(load().csa_enable_peer_access(peer_device), "csa_enable_peer_access")
+
+
+def ipc_export(t: torch.Tensor):
+    """(handle bytes, offset, nbytes) that lets another process of this box map ``t``'s memory (csa_ipc_export)."""
+    _require_cuda(t)
+    h = ctypes.create_string_buffer(64)
+    off = c_int64(0)
+    with torch.cuda.device(t.device):
+        _check(load().csa_ipc_export(t.data_ptr(), h, ctypes.byref(off)), "csa_ipc_export")
+    return bytes(h.raw), int(off.value), t.numel() * t.element_size()
+
+
+class _RawDeviceMemory:
+    """``__cuda_array_interface__`` view of mapped peer memory, so that torch can alias it as a uint8 tensor."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+_IPC_OPEN: dict = {}   # (device index, handle bytes) -> mapped base: an allocation can be opened once per process
+
+
+def ipc_import(handle, device: torch.device) -> torch.Tensor:
+    """Map another process's allocation into ``device``'s address space; returns a uint8 tensor aliasing the exported
+    bytes.  The mapping stays open for the life of the process (the exchange buffers live as long as the job)."""
+    hbytes, off, nbytes = handle
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    with torch.cuda.device(idx):
+        base = _IPC_OPEN.get((idx, hbytes))
+        if base is None:
+            out = c_void_p(0)
+            _check(load().csa_ipc_open(hbytes, ctypes.byref(out)), "csa_ipc_open")
+            base = _IPC_OPEN[(idx, hbytes)] = out.value
+        return torch.as_tensor(_RawDeviceMemory(base + off, nbytes), device=torch.device("cuda", idx))
 
 
 def last_launch() -> dict:

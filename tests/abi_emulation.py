@@ -65,8 +65,13 @@ def gather_kv(k, v, group_rows, n_groups, s_idx, s_count, max_rows):
 
 def attn_fwd(q, o, *, heads, n_groups, n_frames, n_q, k_a=None, v_a=None, a_group_rows=0, k_b=None, v_b=None,
              b_group_rows=0, idx=None, counts=None, list_base=-1, list_step=0, g_adjust=0, ca=(0, 0, 0),
-             cb=(0, 0, 0), scale=None, max_ctas=0, ranges=None, range_base=0, range_step=0):
+             cb=(0, 0, 0), scale=None, max_ctas=0, ranges=None, range_base=0, range_step=0, split=True,
+             b_first=False, ready=None, ready_epoch=0, ready_bounds=None):
     C = q.shape[1]
+    if ready is not None:
+        # the kernel waits per peer when it reaches that peer's rows; the emulation waits for all of them up front
+        for r in range(len(ready_bounds) - 1):
+            _wait_ge(ready, r, ready_epoch, "ready")
     for g in range(n_groups):
         for f in range(n_frames):
             ks, vs = [], []
@@ -96,10 +101,49 @@ def attn_fwd(q, o, *, heads, n_groups, n_frames, n_q, k_a=None, v_a=None, a_grou
     return o
 
 
+def _wait_ge(flags, i, value, what, timeout=120.0):
+    import time
+    t0 = time.time()
+    while int(flags[i]) < value:
+        if time.time() - t0 > timeout:
+            raise TimeoutError(f"{what}[{i}] stayed at {int(flags[i])} < {value}")
+        time.sleep(0.001)
+
+
+def peer_scatter_kv(k, v, idx, count, dst_row0, k_dst, v_dst, ready, self_index, epoch, done, done_epoch, counter):
+    for r in range(len(k_dst)):
+        if r != self_index and done_epoch > 0:
+            _wait_ge(done, r, done_epoch, "done")
+    rows = idx[:count].long()
+    for r in range(len(k_dst)):
+        # poison what a correct reader never touches before the flag is up: the rows are written AFTER a delay only
+        # in the sense that the flag follows them
+        k_dst[r][dst_row0:dst_row0 + count] = k[rows]
+        v_dst[r][dst_row0:dst_row0 + count] = v[rows]
+    for r in range(len(k_dst)):
+        ready[r][self_index] = epoch
+    PEER_LOG.append(("scatter", epoch, count, dst_row0, done_epoch))
+
+
+def peer_signal(done, self_index, epoch, like):
+    for r in range(len(done)):
+        if r != self_index:
+            done[r][self_index] = epoch
+    PEER_LOG.append(("signal", epoch))
+
+
+def enable_peer_access(peer_device):
+    pass
+
+
+PEER_LOG = []
+
+
 def install(monkeypatch_or_none, native, processor_cls=None):
     """Replace the native entry points by the emulations (monkeypatch fixture, or plain setattr when None)."""
     pairs = dict(compact_rows=compact_rows, sample_ranges=sample_ranges, gather_rows=gather_rows,
-                 gather_kv=gather_kv, attn_fwd=attn_fwd)
+                 gather_kv=gather_kv, attn_fwd=attn_fwd, peer_scatter_kv=peer_scatter_kv, peer_signal=peer_signal,
+                 enable_peer_access=enable_peer_access)
     for name, fn in pairs.items():
         if monkeypatch_or_none is None:
             setattr(native, name, fn)

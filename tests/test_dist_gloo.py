@@ -64,10 +64,12 @@ def _run_story(host, procs, attn, xs, slicer):
     return outs
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, exchange="nccl"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.set_num_threads(1)
+    if exchange == "p2p":
+        mp.set_sharing_strategy("file_system")   # peer buffers of the exchange are shared-memory CPU tensors here
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from spider_b200.dist import FrameSharding
@@ -76,7 +78,7 @@ def _worker(rank, world, port, q):
         host.height, host.width, host.total_count = H, W, 2
         cls = make_processor_class(host)
         abi_emulation.install(None, native, cls)
-        sh = FrameSharding(FL, None, torch.device("cpu"))
+        sh = FrameSharding(FL, None, torch.device("cpu"), exchange=exchange)
         procs = [cls(id_length=FL, device="cpu", dtype=torch.float32) for _ in range(2)]
         for p in procs:
             p.dist = sh
@@ -99,15 +101,16 @@ def _worker(rank, world, port, q):
         finally:
             torch.manual_seed = real_seed
         sh.check_lockstep(0.5)
-        q.put((rank, sh.cfg, sh.f0, sh.frames_local, [o.clone() for o in outs], sh.bytes_exchanged,
-               sorted(procs[0].id_bank.keys())))
+        q.put((rank, sh.cfg, sh.f0, sh.frames_local, [o.numpy().copy() for o in outs], sh.bytes_exchanged,
+               sorted(procs[0].id_bank.keys()), list(abi_emulation.PEER_LOG),
+               (sh.peers.allocations, sh.peers.epoch) if sh.peers is not None else None))
     finally:
         dist.barrier()
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_sharded_write_pass_matches_single_process_and_oracle(world, monkeypatch):
+@pytest.mark.parametrize("world,exchange", [(2, "nccl"), (4, "nccl"), (4, "p2p"), (8, "p2p")])
+def test_sharded_write_pass_matches_single_process_and_oracle(world, exchange, monkeypatch):
     # single process, unsharded, same emulated ABI
     host = spider_b200.StoryGlobals()
     host.height, host.width, host.total_count = H, W, 2
@@ -140,7 +143,7 @@ def test_sharded_write_pass_matches_single_process_and_oracle(world, monkeypatch
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q, exchange)) for r in range(world)]
     for p in ps:
         p.start()
     results = [q.get(timeout=240) for _ in range(world)]
@@ -149,15 +152,28 @@ def test_sharded_write_pass_matches_single_process_and_oracle(world, monkeypatch
         assert p.exitcode == 0
     gc = world // 2
     seen = set()
-    for rank, cfg, f0, fr, outs, nbytes, bank_keys in results:
+    for rank, cfg, f0, fr, outs, nbytes, bank_keys, peer_log, peer_state in results:
         assert cfg == rank // gc and fr == FL // gc and f0 == (rank % gc) * fr
         seen.add((cfg, f0))
         for got, ref in zip(outs, single):
             ref_rows = ref[cfg * FL + f0:cfg * FL + f0 + fr]
+            got = torch.from_numpy(got)
             assert got.shape == ref_rows.shape
             assert (got - ref_rows).abs().max().item() < 2e-5
         assert (nbytes > 0) == (gc > 1)          # G == 2 exchanges nothing
         assert bank_keys == [25, 26, 27]
+        if exchange == "p2p" and gc > 1:
+            # one fused scatter + one release signal per consistent layer call; the smaller layer comes first, so the
+            # buffers are allocated twice and the epochs restart with the second allocation
+            n_calls = STEPS * 2
+            assert [e[0] for e in peer_log] == ["scatter", "signal"] * n_calls
+            assert peer_state == (2, n_calls - 1)
+            epochs = [e[1] for e in peer_log if e[0] == "scatter"]
+            assert epochs == [1] + list(range(1, n_calls))
+            # a slot is rewritten only after every peer has released it: done_epoch = epoch - 2
+            assert all(e[4] == max(0, e[1] - 2) for e in peer_log if e[0] == "scatter")
+        else:
+            assert peer_log == [] and peer_state is None
     assert len(seen) == world
 
 
