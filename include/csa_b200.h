@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define CSA_ABI_VERSION 4
+#define CSA_ABI_VERSION 5
 
 #define CSA_E_BADARG (-1)   /* null pointer, non-positive size, misaligned pointer/stride */
 #define CSA_E_SHAPE (-2)    /* unsupported geometry (head_dim != 64, row stride not 16-byte aligned, ...) */
@@ -208,6 +208,12 @@ typedef struct csa_attn_args {
   uint32_t ready_epoch;
   int32_t ready_n;
   int32_t ready_bounds[CSA_MAX_PEERS + 1];
+  /* > 0: the bounds are NOT known on the host — peer r delivers the sampled rows of frames
+   * [r*ready_frames_per_peer, (r+1)*ready_frames_per_peer), and the kernel derives the bounds from `ranges`
+   * (ranges[f] = {0, lo_f, hi_f, ..}: bound r = lo of frame r*fpp, last bound = hi of the last frame), so that a step
+   * needs no host read-back of the sampled counts.  ready_bounds is ignored. */
+  int32_t ready_frames_per_peer;
+  int32_t _pad2;
 } csa_attn_args_t;
 
 #define CSA_ATTN_NO_SPLIT 1 /* flags: process every unit whole even if a workspace is given */
@@ -264,6 +270,14 @@ typedef struct csa_peer_scatter_args {
   uint32_t done_epoch;
   const uint32_t* done; /* LOCAL uint32[n_peers], written by the peers */
   uint32_t* counter;    /* LOCAL, zero */
+  /* Optional, device-side geometry (no host read-back of the sampled counts): when `ranges` (csa_sample_ranges
+   * output) is given, `idx` is the WHOLE sampled list S, this GPU owns frames [self*frames_per_peer, +frames_per_peer)
+   * and the kernel takes  dst_row0 = lo of its first frame,  count = hi of its last frame - dst_row0,  source row of
+   * entry i = idx[dst_row0 + i] + idx_adjust  (idx_adjust = -first_frame*block_n turns a position in the half's
+   * key sequence into a row of the local k / v); `count` is then only an upper bound used to size the grid. */
+  const int32_t* ranges;
+  int32_t frames_per_peer;
+  int32_t idx_adjust;
 } csa_peer_scatter_args_t;
 
 int csa_peer_scatter_kv(const csa_peer_scatter_args_t* args, void* stream);

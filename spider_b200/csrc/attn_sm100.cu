@@ -140,6 +140,7 @@ struct AttnKernelParams {
   uint32_t ready_epoch;
   int32_t ready_n;
   int32_t ready_bounds[CSA_MAX_PEERS + 1];
+  int32_t ready_fpp;  // > 0: bounds come from `ranges` (frames per peer), not from ready_bounds
   int32_t b_first;  // key order of a unit: contiguous B segment first, then the runs of A
 };
 
@@ -359,7 +360,16 @@ __device__ __forceinline__ void producer_warp(const AttnKernelParams& p, const u
           const int lo = row0 - w.a_base;
           const int hi = min(lo + kBN, srow - w.a_base + slen);
           for (int r = 0; r < p.ready_n; ++r) {
-            if (((confirmed >> r) & 1u) == 0u && p.ready_bounds[r] < hi && p.ready_bounds[r + 1] > lo) {
+            if ((confirmed >> r) & 1u) continue;
+            int b0, b1;
+            if (p.ready_fpp > 0) {
+              b0 = __ldg(p.ranges + 4 * (r * p.ready_fpp) + 1);
+              b1 = __ldg(p.ranges + 4 * ((r + 1) * p.ready_fpp - 1) + 2);
+            } else {
+              b0 = p.ready_bounds[r];
+              b1 = p.ready_bounds[r + 1];
+            }
+            if (b0 < hi && b1 > lo) {
               flag_wait_ge(p.ready + r, p.ready_epoch, 0x130 + r, p.dbg);
               confirmed |= 1u << r;
             }
@@ -927,9 +937,14 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
     if (a->ready_n <= 0 || a->ready_n > CSA_MAX_PEERS || (reinterpret_cast<uintptr_t>(a->ready) & 3))
       return set_error(CSA_E_BADARG, "csa_attn_fwd: ready_n must be in [1, %d] and ready 4-byte aligned", CSA_MAX_PEERS);
     if (use_g) return set_error(CSA_E_BADARG, "csa_attn_fwd: arrival flags cover contiguous runs of A only, not index lists");
-    for (int r = 0; r < a->ready_n; ++r)
-      if (a->ready_bounds[r] > a->ready_bounds[r + 1])
-        return set_error(CSA_E_BADARG, "csa_attn_fwd: ready_bounds must be non-decreasing");
+    if (a->ready_frames_per_peer > 0) {
+      if (!use_r) return set_error(CSA_E_BADARG, "csa_attn_fwd: ready_frames_per_peer needs ranges");
+      p.ready_fpp = a->ready_frames_per_peer;
+    } else {
+      for (int r = 0; r < a->ready_n; ++r)
+        if (a->ready_bounds[r] > a->ready_bounds[r + 1])
+          return set_error(CSA_E_BADARG, "csa_attn_fwd: ready_bounds must be non-decreasing");
+    }
     p.ready = a->ready;
     p.ready_epoch = a->ready_epoch;
     p.ready_n = a->ready_n;
@@ -990,9 +1005,15 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
 
   const size_t smem = sizeof(AttnSmem) + 1024;
   auto kern = a->dtype == CSA_DTYPE_BF16 ? csa_attn_kernel<true> : csa_attn_kernel<false>;
-  ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (ce != cudaSuccess)
-    return set_error(static_cast<int>(ce), "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(ce));
+  // per device and kernel instantiation, once (the attribute is sticky; the call costs a few microseconds)
+  static bool smem_set[64][2];
+  const int ki = a->dtype == CSA_DTYPE_BF16 ? 1 : 0;
+  if (dev < 0 || dev >= 64 || !smem_set[dev][ki]) {
+    ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (ce != cudaSuccess)
+      return set_error(static_cast<int>(ce), "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(ce));
+    if (dev >= 0 && dev < 64) smem_set[dev][ki] = true;
+  }
   kern<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_error(static_cast<int>(ce), "csa_attn_kernel launch: %s", cudaGetErrorString(ce));

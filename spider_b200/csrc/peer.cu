@@ -25,6 +25,8 @@ struct PeerScatterParams {
   const uint32_t* done;
   uint32_t* counter;
   uint32_t* dbg;
+  const int32_t* ranges;
+  int32_t frames_per_peer, idx_adjust;
 };
 
 // one warp per (row, K|V): the row is read once (16 B per lane per step) and stored to every peer
@@ -34,14 +36,26 @@ __global__ void __launch_bounds__(256) peer_scatter_kernel(const __grid_constant
     flag_wait_ge(p.done + threadIdx.x, p.done_epoch, 0x400 + threadIdx.x, p.dbg);
   __syncthreads();
 
+  // geometry: from the host, or from the device-resident runs of the sampled list
+  int count = p.count, dst_row0 = p.dst_row0, adjust = 0;
+  const int32_t* idx = p.idx;
+  if (p.ranges != nullptr) {
+    const int4 first = __ldg(reinterpret_cast<const int4*>(p.ranges) + p.self * p.frames_per_peer);
+    const int4 last = __ldg(reinterpret_cast<const int4*>(p.ranges) + (p.self + 1) * p.frames_per_peer - 1);
+    dst_row0 = first.y;
+    count = last.z - first.y;
+    idx = p.idx + dst_row0;
+    adjust = p.idx_adjust;
+  }
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int vecs = p.row_bytes >> 4;
-  for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < 2 * p.count; i += gridDim.x * warps_per_block) {
+  for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < 2 * count; i += gridDim.x * warps_per_block) {
     const int row = i >> 1;
     const bool is_v = i & 1;
-    const uint4* s = reinterpret_cast<const uint4*>((is_v ? p.v : p.k) + static_cast<int64_t>(__ldg(p.idx + row)) * p.ld);
-    const int64_t off = static_cast<int64_t>(p.dst_row0 + row) * p.dst_ld;
+    const uint4* s =
+        reinterpret_cast<const uint4*>((is_v ? p.v : p.k) + static_cast<int64_t>(__ldg(idx + row) + adjust) * p.ld);
+    const int64_t off = static_cast<int64_t>(dst_row0 + row) * p.dst_ld;
     for (int c = lane; c < vecs; c += 32) {
       const uint4 x = __ldg(s + c);
 #pragma unroll
@@ -122,6 +136,13 @@ extern "C" int csa_peer_scatter_kv(const csa_peer_scatter_args_t* a, void* strea
   p.done = a->done;
   p.counter = a->counter;
   p.dbg = debug_record_devptr();
+  if (a->ranges != nullptr) {
+    if (a->frames_per_peer <= 0 || (reinterpret_cast<uintptr_t>(a->ranges) & 15) || !a->idx)
+      return set_error(CSA_E_BADARG, "csa_peer_scatter_kv: ranges need frames_per_peer > 0, 16-byte alignment and idx");
+    p.ranges = a->ranges;
+    p.frames_per_peer = a->frames_per_peer;
+    p.idx_adjust = a->idx_adjust;
+  }
   const int warps_per_block = 8;
   int grid = (2 * a->count + warps_per_block - 1) / warps_per_block;
   const int cap = 148 * 4;  // all blocks resident (the first thing a block does is wait for the peers)

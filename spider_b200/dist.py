@@ -77,6 +77,7 @@ class PeerExchange:
         self.bufs = None      # per rank: uint8 tensor [SLOTS * 2 * cap_bytes]
         self.flags = None     # per rank: int32 tensor [3, CSA_MAX_PEERS]: ready, done, {counter, ...}
         self._keep = None
+        self._views = {}
         self.allocations = 0
 
     def ensure(self, need_bytes: int) -> None:
@@ -105,12 +106,20 @@ class PeerExchange:
             self.bufs.append(b)
             self.flags.append(f.view(torch.int32).view(3, native.CSA_MAX_PEERS))
         self.cap_bytes = cap
+        self._views = {}
+        self._ready = [f[0] for f in self.flags]
+        self._done = [f[1] for f in self.flags]
+        self._counter = self.flags[me][2]
         self.epoch = 0    # fresh flags: epochs restart
         self.allocations += 1
         dist.barrier(group=sh.half_group)          # every rank has mapped every buffer before the first store
 
     def views(self, slot: int, rows: int, cols: int, dtype):
-        """Per rank the (K[S], V[S]) views [rows, cols] of ``slot``."""
+        """Per rank the (K[S], V[S]) views [rows, cols] of ``slot`` (cached: the same few layer shapes recur)."""
+        key = (slot, rows, cols, dtype)
+        hit = self._views.get(key)
+        if hit is not None:
+            return hit
         nbytes = rows * cols * torch.empty((), dtype=dtype).element_size()
         if nbytes > self.cap_bytes:
             raise ValueError("PeerExchange.ensure() was not called for this layer size")
@@ -120,43 +129,50 @@ class PeerExchange:
             v0 = (slot * 2 + 1) * self.cap_bytes
             ks.append(b[k0:k0 + nbytes].view(dtype).view(rows, cols))
             vs.append(b[v0:v0 + nbytes].view(dtype).view(rows, cols))
+        self._views[key] = (ks, vs)
         return ks, vs
 
     def ready(self):
-        return [f[0] for f in self.flags]
+        return self._ready
 
     def done(self):
-        return [f[1] for f in self.flags]
+        return self._done
 
     def counter(self):
-        return self.flags[self.sh.rank_in_half][2]
+        return self._counter
 
 
 class ShardPlan:
-    """Per (mask, sharding): who sends how many sampled rows, and where they land in the compact buffer."""
+    """Per (mask, sharding): the device-resident sampled list and its per-frame runs; on demand (NCCL path and
+    reporting only — it costs a host read-back) who sends how many sampled rows and where they land."""
 
     def __init__(self, cm, sh: "FrameSharding", device):
-        F, N = cm.id_length, cm.n_tokens
-        s_idx, s_count, ranges = cm.sample_list(device)
-        rh = ranges.cpu().tolist()                     # the one host sync per mask
-        self.s_idx, self.s_count, self.ranges = s_idx, s_count, ranges
-        self.total = int(rh[F][1])
-        fr = sh.frames_local
-        # run of S that falls into the frames of rank r of this half: [lo_r, hi_r)
-        self.lo = [rh[r * fr][1] for r in range(sh.gc)]
-        self.hi = [rh[r * fr + fr - 1][2] for r in range(sh.gc)]
-        self.counts = [h - l for l, h in zip(self.lo, self.hi)]
-        self.pad = max(8, (max(self.counts) + 7) // 8 * 8)
-        me = sh.rank_in_half
-        self.count_me = self.counts[me]
-        # positions of my sampled rows inside my local K/V (frames f0 .. f0+fr-1 are rows [0, fr*N))
-        self.local_idx = (s_idx[self.lo[me]:self.hi[me]] - sh.f0 * N).contiguous()
-        # compact position i of S -> row of the all-gathered slab matrix [(rank, K|V, pad rows), C]
-        parts = [torch.arange(c, dtype=torch.int32, device=device) + 2 * r * self.pad
-                 for r, c in enumerate(self.counts)]
-        self.slab_map = torch.cat(parts) if parts else torch.zeros((0,), dtype=torch.int32, device=device)
-        # rows [bounds[r], bounds[r+1]) of the S-ordered buffer are the sampled rows of rank r's frames
-        self.bounds = [self.lo[r] for r in range(sh.gc)] + [self.hi[sh.gc - 1]]
+        self.cm, self.sh, self.device = cm, sh, device
+        self.s_idx, self.s_count, self.ranges = cm.sample_list(device)
+        self._host = None
+
+    def host(self) -> "ShardPlan":
+        if self._host is None:
+            sh, device = self.sh, self.device
+            F, N = self.cm.id_length, self.cm.n_tokens
+            rh = self.ranges.cpu().tolist()                # host sync
+            self.total = int(rh[F][1])
+            fr = sh.frames_local
+            # run of S that falls into the frames of rank r of this half: [lo_r, hi_r)
+            self.lo = [rh[r * fr][1] for r in range(sh.gc)]
+            self.hi = [rh[r * fr + fr - 1][2] for r in range(sh.gc)]
+            self.counts = [h - l for l, h in zip(self.lo, self.hi)]
+            self.pad = max(8, (max(self.counts) + 7) // 8 * 8)
+            me = sh.rank_in_half
+            self.count_me = self.counts[me]
+            # positions of my sampled rows inside my local K/V (frames f0 .. f0+fr-1 are rows [0, fr*N))
+            self.local_idx = (self.s_idx[self.lo[me]:self.hi[me]] - sh.f0 * N).contiguous()
+            # compact position i of S -> row of the all-gathered slab matrix [(rank, K|V, pad rows), C]
+            parts = [torch.arange(c, dtype=torch.int32, device=device) + 2 * r * self.pad
+                     for r, c in enumerate(self.counts)]
+            self.slab_map = torch.cat(parts) if parts else torch.zeros((0,), dtype=torch.int32, device=device)
+            self._host = True
+        return self
 
 
 class FrameSharding:
@@ -193,7 +209,16 @@ class FrameSharding:
                 g = dist.new_group(ranks=[world_ranks[c * self.gc + i] for i in range(self.gc)])
                 if c == self.cfg:
                     self.half_group = g
-        self.bytes_exchanged = 0                  # received bytes, for reporting
+        self._bytes_exchanged = 0                 # received bytes, for reporting
+        self._p2p_sent = {}                       # id(plan) -> [plan, bytes per sampled row sent so far] (lazy)
+
+    @property
+    def bytes_exchanged(self) -> int:
+        """Bytes this rank sent to its peers so far (reporting; reads the sampled counts back, so not for hot loops)."""
+        total = self._bytes_exchanged
+        for plan, per_row in self._p2p_sent.values():
+            total += plan.host().count_me * per_row
+        return total
 
     # ---------------------------------------------------------------------------------------------- lock-step
     def sync_masks(self, *masks) -> None:
@@ -238,6 +263,7 @@ class FrameSharding:
         pl = self.plan(cm, q.device)
         if self.gc > 1 and self.exchange == "p2p":
             return self._attn_write_p2p(q, k, v, o, N, heads, pl, Fl)
+        pl.host()
         if self.gc == 1:
             # one CFG half per GPU: everything is local, same as the single-GPU path with one group
             k_s, v_s, cap = native.gather_kv(k, v, Fl * N, 1, pl.s_idx, pl.s_count, Fl * N)
@@ -248,7 +274,7 @@ class FrameSharding:
                 native.gather_rows(v, pl.local_idx, pl.count_me, out=send[1])
             recv = torch.empty((self.gc, 2, pl.pad, C), dtype=k.dtype, device=k.device)
             dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.half_group)
-            self.bytes_exchanged += (self.gc - 1) * send.numel() * send.element_size()
+            self._bytes_exchanged += (self.gc - 1) * send.numel() * send.element_size()
             flat = recv.view(-1, C)
             # slab rows -> the compact K[S], V[S] buffers of the single-GPU path (zero tail included)
             k_s, v_s, cap = native.gather_kv(flat[:-pl.pad], flat[pl.pad:], flat.shape[0] - pl.pad, 1, pl.slab_map,
@@ -273,13 +299,17 @@ class FrameSharding:
         ex.epoch += 1
         epoch = ex.epoch
         ks, vs = ex.views(epoch % ex.SLOTS, rows, C, k.dtype)
-        # peers last read this slot in epoch - SLOTS
-        native.peer_scatter_kv(k, v, pl.local_idx, pl.count_me, pl.lo[me], ks, vs, ex.ready(), me, epoch,
-                               ex.done()[me], max(0, epoch - ex.SLOTS), ex.counter())
-        self.bytes_exchanged += (self.gc - 1) * 2 * pl.count_me * C * k.element_size()
+        # Geometry stays on the device (no read-back of the sampled counts): the scatter kernel finds this rank's run
+        # of S in `ranges`, the attention kernel the peers' bounds.  Peers last read this slot in epoch - SLOTS.
+        native.peer_scatter_kv(k, v, pl.s_idx, fr * N, 0, ks, vs, ex.ready(), me, epoch,
+                               ex.done()[me], max(0, epoch - ex.SLOTS), ex.counter(),
+                               ranges=pl.ranges, frames_per_peer=fr, idx_adjust=-self.f0 * N)
+        sent = self._p2p_sent.setdefault(id(pl), [pl, 0])
+        sent[1] += (self.gc - 1) * 2 * C * k.element_size()
         native.attn_fwd(q, o, heads=heads, n_groups=1, n_frames=fr, n_q=N,
                         k_a=ks[me], v_a=vs[me], a_group_rows=rows, ranges=pl.ranges, range_base=self.f0,
                         range_step=1, k_b=k, v_b=v, b_group_rows=fr * N, cb=(0, N, N),
-                        b_first=True, ready=ex.ready()[me], ready_epoch=epoch, ready_bounds=pl.bounds)
+                        b_first=True, ready=ex.ready()[me], ready_epoch=epoch, ready_peers=self.gc,
+                        ready_frames_per_peer=fr)
         native.peer_signal(ex.done(), me, epoch, q)
         return o

@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CSA_B200_LIB: developer knob to load an experimental build of the same ABI (kernel tuning sweeps); default in-tree
 LIB_PATH = os.environ.get("CSA_B200_LIB") or os.path.join(_HERE, "libcsa_b200.so")
 
-CSA_ABI_VERSION = 4
+CSA_ABI_VERSION = 5
 CSA_DTYPE_F16 = 0
 CSA_DTYPE_BF16 = 1
 CSA_TILE = 128
@@ -105,6 +105,8 @@ class CsaAttnArgs(ctypes.Structure):
         ("ready_epoch", c_uint32),
         ("ready_n", c_int32),
         ("ready_bounds", c_int32 * (CSA_MAX_PEERS + 1)),
+        ("ready_frames_per_peer", c_int32),
+        ("_pad2", c_int32),
     ]
 
 
@@ -130,6 +132,9 @@ class CsaPeerScatterArgs(ctypes.Structure):
         ("done_epoch", c_uint32),
         ("done", c_void_p),
         ("counter", c_void_p),
+        ("ranges", c_void_p),
+        ("frames_per_peer", c_int32),
+        ("idx_adjust", c_int32),
     ]
 
 
@@ -386,7 +391,8 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
              ca: tuple = (0, 0, 0), cb: tuple = (0, 0, 0), scale: Optional[float] = None,
              max_ctas: int = 0, ranges: Optional[torch.Tensor] = None, range_base: int = 0,
              range_step: int = 0, split=True, b_first: bool = False, ready: Optional[torch.Tensor] = None,
-             ready_epoch: int = 0, ready_bounds=None) -> torch.Tensor:
+             ready_epoch: int = 0, ready_bounds=None, ready_peers: int = 0,
+             ready_frames_per_peer: int = 0) -> torch.Tensor:
     """Launch csa_attn_fwd on the current stream.  All matrices are 2-D ``(rows, heads*64)`` with unit column stride."""
     _require_cuda(q, o)
     ensure_device(q.device)
@@ -428,12 +434,17 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
         a.flags |= CSA_ATTN_B_FIRST
     if ready is not None:
         # rows [ready_bounds[r], ready_bounds[r+1]) of A are delivered by peer r (peer_scatter_kv on that GPU)
-        n = len(ready_bounds) - 1
+        # (or, with ready_frames_per_peer, the sampled rows of that many frames each: bounds taken from `ranges` on
+        # the device — no host read-back)
+        n = ready_peers if ready_frames_per_peer > 0 else len(ready_bounds) - 1
         if ready.dtype != torch.int32 or not ready.is_contiguous() or ready.numel() < n or not 1 <= n <= CSA_MAX_PEERS:
             raise CsaNativeError("ready must be a contiguous int32 tensor with one flag per peer (<= 8 peers)")
         a.ready, a.ready_epoch, a.ready_n = ready.data_ptr(), ready_epoch, n
-        for i, b in enumerate(ready_bounds):
-            a.ready_bounds[i] = b
+        if ready_frames_per_peer > 0:
+            a.ready_frames_per_peer = ready_frames_per_peer
+        else:
+            for i, b in enumerate(ready_bounds):
+                a.ready_bounds[i] = b
     stream = _stream_ptr(q)
     if split:
         ws = attn_workspace(q.device, stream)
@@ -457,10 +468,12 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
 
 def peer_scatter_kv(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, count: int, dst_row0: int, k_dst, v_dst,
                     ready, self_index: int, epoch: int, done: torch.Tensor, done_epoch: int,
-                    counter: torch.Tensor) -> None:
+                    counter: torch.Tensor, ranges: Optional[torch.Tensor] = None, frames_per_peer: int = 0,
+                    idx_adjust: int = 0) -> None:
     """Store this GPU's sampled K/V rows into the S-ordered buffers of every GPU of the group and raise its arrival
     flag there (see csa_peer_scatter_kv).  ``k_dst / v_dst / ready`` are lists of tensors, one per GPU (peer memory;
-    entry ``self_index`` is local); ``done`` and ``counter`` are local."""
+    entry ``self_index`` is local); ``done`` and ``counter`` are local.  With ``ranges`` the geometry is read on the
+    device (``idx`` = the whole sampled list, ``count`` = an upper bound, ``dst_row0`` ignored)."""
     _require_cuda(k, v, done, counter)
     ensure_device(k.device)
     n = len(k_dst)
@@ -480,7 +493,7 @@ def peer_scatter_kv(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, count: 
         if kd.dim() != 2 or kd.stride(1) != 1 or kd.shape[1] != k.shape[1] or kd.dtype != k.dtype or \
                 vd.shape != kd.shape or vd.stride(0) != kd.stride(0) or (ld is not None and kd.stride(0) != ld):
             raise CsaNativeError("peer_scatter_kv: destination buffers must be 2-D, of k's width/dtype and one stride")
-        if dst_row0 + count > kd.shape[0]:
+        if (0 if ranges is not None else dst_row0) + count > kd.shape[0]:
             raise CsaNativeError(f"peer_scatter_kv: rows [{dst_row0}, {dst_row0 + count}) exceed the buffer "
                                  f"({kd.shape[0]} rows)")
         ld = kd.stride(0)
@@ -488,6 +501,8 @@ def peer_scatter_kv(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, count: 
     a.dst_ld_bytes = ld * es
     a.epoch, a.done_epoch = epoch, done_epoch
     a.done, a.counter = done.data_ptr(), counter.data_ptr()
+    if ranges is not None:
+        a.ranges, a.frames_per_peer, a.idx_adjust = ranges.data_ptr(), frames_per_peer, idx_adjust
     _check(load().csa_peer_scatter_kv(ctypes.byref(a), _stream_ptr(k)), "csa_peer_scatter_kv")
     LAUNCHES["csa_peer_scatter_kv"] += 1
 

@@ -66,11 +66,11 @@ def gather_kv(k, v, group_rows, n_groups, s_idx, s_count, max_rows):
 def attn_fwd(q, o, *, heads, n_groups, n_frames, n_q, k_a=None, v_a=None, a_group_rows=0, k_b=None, v_b=None,
              b_group_rows=0, idx=None, counts=None, list_base=-1, list_step=0, g_adjust=0, ca=(0, 0, 0),
              cb=(0, 0, 0), scale=None, max_ctas=0, ranges=None, range_base=0, range_step=0, split=True,
-             b_first=False, ready=None, ready_epoch=0, ready_bounds=None):
+             b_first=False, ready=None, ready_epoch=0, ready_bounds=None, ready_peers=0, ready_frames_per_peer=0):
     C = q.shape[1]
     if ready is not None:
         # the kernel waits per peer when it reaches that peer's rows; the emulation waits for all of them up front
-        for r in range(len(ready_bounds) - 1):
+        for r in range(ready_peers if ready_frames_per_peer > 0 else len(ready_bounds) - 1):
             _wait_ge(ready, r, ready_epoch, "ready")
     for g in range(n_groups):
         for f in range(n_frames):
@@ -110,10 +110,15 @@ def _wait_ge(flags, i, value, what, timeout=120.0):
         time.sleep(0.001)
 
 
-def peer_scatter_kv(k, v, idx, count, dst_row0, k_dst, v_dst, ready, self_index, epoch, done, done_epoch, counter):
+def peer_scatter_kv(k, v, idx, count, dst_row0, k_dst, v_dst, ready, self_index, epoch, done, done_epoch, counter,
+                    ranges=None, frames_per_peer=0, idx_adjust=0):
     for r in range(len(k_dst)):
         if r != self_index and done_epoch > 0:
             _wait_ge(done, r, done_epoch, "done")
+    if ranges is not None:   # device-side geometry of the ABI: this rank's run of the sampled list
+        dst_row0 = int(ranges[self_index * frames_per_peer][1])
+        count = int(ranges[(self_index + 1) * frames_per_peer - 1][2]) - dst_row0
+        idx = idx[dst_row0:dst_row0 + count] + idx_adjust
     rows = idx[:count].long()
     for r in range(len(k_dst)):
         # poison what a correct reader never touches before the flag is up: the rows are written AFTER a delay only
