@@ -576,12 +576,11 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
     for (int u = blockIdx.x; u < p.n_sched; u += gridDim.x) {
       const Unit w = decode_unit(p, u);
       const int nt = w.nt;
-      const int q_in_frame = w.qp * (2 * kBM) + s * kBM + row;
-      const bool row_ok = q_in_frame < p.n_q;
-      uint4* optr = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
-                                             static_cast<int64_t>(w.q_row0 + s * kBM + row) * p.o_ld + w.h * kHD);
       TRACE(10);
       if (w.total == 0) {  // no key at all (never split: every piece of such a unit lands here)
+        const bool row_ok = w.qp * (2 * kBM) + s * kBM + row < p.n_q;
+        uint4* optr = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
+                                               static_cast<int64_t>(w.q_row0 + s * kBM + row) * p.o_ld + w.h * kHD);
         if (row_ok && (w.piece < 0 || w.t0 == 0)) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) optr[i] = make_uint4(0, 0, 0, 0);
@@ -722,7 +721,16 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       }
       TRACE(12);
       od += nt;
-      if (w.piece < 0) {
+      // Where the result goes is decoded again here instead of being carried through the tile loop: the loop runs
+      // at the register limit (a 128-key score row per thread), and anything live across it is spilled or
+      // rematerialised on the latency chain of every tile.
+      int u_epi = u;
+      asm volatile("" : "+r"(u_epi));
+      const Unit e = decode_unit(p, u_epi);
+      const bool row_ok = e.qp * (2 * kBM) + s * kBM + row < p.n_q;
+      uint4* optr = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
+                                             static_cast<int64_t>(e.q_row0 + s * kBM + row) * p.o_ld + e.h * kHD);
+      if (e.piece < 0) {
         // whole unit: normalise, store
         const float inv = 1.0f / l;
 #pragma unroll
@@ -747,7 +755,7 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         // piece of a split unit: leave the unnormalised partial (O, m, l) of this row in the workspace; the CTA
         // that delivers the last piece of the unit (arrival counter) merges all of them — nobody waits for anybody
         const int prow = s * kBM + row;
-        float* part = p.ws + static_cast<int64_t>(w.piece) * kPieceFloats;
+        float* part = p.ws + static_cast<int64_t>(e.piece) * kPieceFloats;
         if (nt > 0) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -765,15 +773,15 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         __threadfence();
         named_bar_sync(9, kThreads - 128);  // all softmax threads of the CTA have published their rows
         if (threadIdx.x == 128) {
-          const uint32_t prev = atomicAdd(p.ws_count + w.split_unit, 1u);
+          const uint32_t prev = atomicAdd(p.ws_count + e.split_unit, 1u);
           const bool last = prev == static_cast<uint32_t>(p.split) - 1u;
-          if (last) p.ws_count[w.split_unit] = 0u;  // ready for the next launch
+          if (last) p.ws_count[e.split_unit] = 0u;  // ready for the next launch
           sm.merge_flag = last ? 1u : 0u;
         }
         named_bar_sync(9, kThreads - 128);
         if (sm.merge_flag != 0u) {
           __threadfence();
-          const float* base = p.ws + static_cast<int64_t>(w.piece - (w.piece % p.split)) * kPieceFloats;
+          const float* base = p.ws + static_cast<int64_t>(e.piece - (e.piece % p.split)) * kPieceFloats;
           float mm = -INFINITY;
           for (int i = 0; i < p.split; ++i)
             mm = fmaxf(mm, __ldcg(base + static_cast<int64_t>(i) * kPieceFloats + 2 * kBM * kHD + prow));

@@ -65,11 +65,13 @@ __global__ void __launch_bounds__(256) peer_scatter_kernel(const __grid_constant
     }
   }
 
-  // publish: every thread's stores are ordered before its fence, the block's before the counter, and the last
-  // block's release stores come after all of them
-  __threadfence_system();
+  // publish (the grid-barrier idiom): the block's stores are ordered before thread 0's system-scope fence by the
+  // CTA barrier (fences are cumulative), the fence before the counter, and the last block's release stores come
+  // after every block's counter increment.  One fence per block instead of one per thread: a system-scope fence
+  // waits for the acknowledgement of all of the thread's remote stores.
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const uint32_t prev = atomicAdd(p.counter, 1u);
     if (prev == gridDim.x - 1) {
       *p.counter = 0u;
