@@ -260,6 +260,7 @@ def run_b200_arm(args):
     host.total_count = len(plan)
     host.write = True
     cls = make_processor_class(host)
+    cls.native_projections = not args.module_projections
 
     sharding = None
     units_local = 2 * Fl
@@ -317,6 +318,7 @@ def run_b200_arm(args):
             # ------------------------------------------------------------------ value: device-resident inputs
             native.reset_launch_counters()
             native.ATTN_EVENTS = []
+            native.prepare_event_pool(2 * len(plan) * args.steps + 8)   # timing events exist before the timed region
             sampler = ClockSampler(local_rank) if rank == 0 else None
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
@@ -526,6 +528,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
                     help="N >= 4: how the sampled K/V rows travel between the GPUs of a CFG half (spider_b200/dist.py)")
+    ap.add_argument("--module-projections", action="store_true",
+                    help="project through the attn module's nn.Linear layers instead of the library's batched "
+                         "csa_linear calls (A/B of the host overhead)")
     ap.add_argument("--host-profile", default="", help="rank 0: cProfile of the timed loop written to this file")
     args = ap.parse_args()
     if args.impl == "reference":

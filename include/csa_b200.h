@@ -17,6 +17,9 @@
  *                            torch.cat of bank and current frames at :92 (two K/V sources are read in place).
  *   csa_gather_rows       <- the row selection implied by the mask when K/V rows have to be materialised
  *                            contiguously (multi-GPU exchange of the sampled rows; bank export).
+ *   csa_linear            <- attn.to_q / to_k / to_v / to_out[0] (Comic_Generation.py:155,164-165,185): the projections
+ *                            either side of the attention, as library GEMMs issued from inside the library.
+ *   csa_run_batch         <- a whole processor call (:129-196) issued with one call into the library.
  *   csa_peer_scatter_kv,  <- (no reference counterpart: the reference is single-GPU) the per-layer exchange of the
  *   csa_peer_signal          sampled K/V rows between the GPUs that share one CFG half, fused with their gather:
  *                            rows are stored straight into every peer's K[S], V[S] buffer over NVLink and the
@@ -40,7 +43,7 @@
 extern "C" {
 #endif
 
-#define CSA_ABI_VERSION 5
+#define CSA_ABI_VERSION 6
 
 #define CSA_E_BADARG (-1)   /* null pointer, non-positive size, misaligned pointer/stride */
 #define CSA_E_SHAPE (-2)    /* unsupported geometry (head_dim != 64, row stride not 16-byte aligned, ...) */
@@ -289,6 +292,77 @@ int csa_peer_signal(uint32_t* const* done, int32_t n_peers, int32_t self, uint32
 /* Enable loads/stores from the current device to memory of `peer_device` (cudaDeviceEnablePeerAccess; already
  * enabled is not an error).  Host-side setup helper. */
 int csa_enable_peer_access(int32_t peer_device);
+
+/*
+ * The projections either side of the attention: y[M,N] = x[M,K] * w[N,K]^T (+ bias[N]) — attn.to_q / to_k / to_v
+ * (Comic_Generation.py:155,164-165; bias-free in SDXL) and attn.to_out[0] (:185, with bias), with the row-major layouts
+ * of torch's nn.Linear (x, y: leading dimension in elements; w: the module's (out_features, in_features) weight).  A
+ * plain library GEMM (cuBLASLt, fp32 accumulation, bias in the epilogue); a weight made of several modules' rows
+ * (K and V stacked: N = 2C) projects them in one launch.  `workspace` (device, 16-byte aligned; may be NULL) is
+ * cuBLASLt's scratch; nothing is allocated on the device.  Returns 1000 + cublasStatus_t on a cuBLAS failure.
+ */
+typedef struct csa_linear_args {
+  uint32_t struct_size; /* sizeof(csa_linear_args_t), checked */
+  int32_t dtype;        /* CSA_DTYPE_* of x, w, bias and y */
+  int64_t m, n, k;
+  const void* x;
+  int64_t ldx;
+  const void* w;
+  int64_t ldw;
+  const void* bias; /* NULL = none */
+  void* y;
+  int64_t ldy;
+  void* workspace;
+  int64_t workspace_bytes;
+} csa_linear_args_t;
+
+int csa_linear(const csa_linear_args_t* args, void* stream);
+
+/*
+ * One processor call = one call into the library: the entries are executed in order on `stream` (projections, K/V
+ * gather or peer exchange, attention, output projection), stopping at the first failure (*failed_index = its
+ * position, -1 if none; may be NULL).  Purely a host-overhead device: the launches are the ones the single entry
+ * points make.  CSA_CALL_EVENT_RECORD records the cudaEvent_t passed as `args` (kernel timing inside a batch).
+ */
+#define CSA_CALL_LINEAR 1
+#define CSA_CALL_ATTN 2
+#define CSA_CALL_GATHER_KV 3
+#define CSA_CALL_PEER_SCATTER 4
+#define CSA_CALL_PEER_SIGNAL 5
+#define CSA_CALL_EVENT_RECORD 6
+
+typedef struct csa_gather_kv_args { /* the arguments of csa_gather_kv, in its order */
+  const void* k;
+  const void* v;
+  int64_t ld_bytes;
+  int32_t group_rows;
+  int32_t n_groups;
+  const int32_t* s_idx;
+  const int32_t* s_count;
+  int32_t max_rows;
+  int32_t _pad0;
+  void* k_out;
+  void* v_out;
+  int64_t out_ld_bytes;
+  int32_t out_group_rows;
+  int32_t row_bytes;
+} csa_gather_kv_args_t;
+
+typedef struct csa_peer_signal_args { /* the arguments of csa_peer_signal */
+  uint32_t* done[CSA_MAX_PEERS];
+  int32_t n_peers;
+  int32_t self;
+  uint32_t epoch;
+  uint32_t _pad0;
+} csa_peer_signal_args_t;
+
+typedef struct csa_call {
+  int32_t kind; /* CSA_CALL_* */
+  int32_t _pad0;
+  const void* args; /* the matching *_args_t (or the cudaEvent_t itself for CSA_CALL_EVENT_RECORD) */
+} csa_call_t;
+
+int csa_run_batch(const csa_call_t* calls, int32_t n_calls, void* stream, int32_t* failed_index);
 
 /*
  * Host-side setup helpers for the peer exchange (one process per GPU): export a device allocation of this process

@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CSA_B200_LIB: developer knob to load an experimental build of the same ABI (kernel tuning sweeps); default in-tree
 LIB_PATH = os.environ.get("CSA_B200_LIB") or os.path.join(_HERE, "libcsa_b200.so")
 
-CSA_ABI_VERSION = 5
+CSA_ABI_VERSION = 6
 CSA_DTYPE_F16 = 0
 CSA_DTYPE_BF16 = 1
 CSA_TILE = 128
@@ -47,6 +47,8 @@ EXPORTED_SYMBOLS = (
     "csa_ipc_export",
     "csa_ipc_open",
     "csa_ipc_close",
+    "csa_linear",
+    "csa_run_batch",
 )
 
 
@@ -138,6 +140,69 @@ class CsaPeerScatterArgs(ctypes.Structure):
     ]
 
 
+class CsaLinearArgs(ctypes.Structure):
+    """Mirror of ``csa_linear_args_t``."""
+
+    _fields_ = [
+        ("struct_size", c_uint32),
+        ("dtype", c_int32),
+        ("m", c_int64),
+        ("n", c_int64),
+        ("k", c_int64),
+        ("x", c_void_p),
+        ("ldx", c_int64),
+        ("w", c_void_p),
+        ("ldw", c_int64),
+        ("bias", c_void_p),
+        ("y", c_void_p),
+        ("ldy", c_int64),
+        ("workspace", c_void_p),
+        ("workspace_bytes", c_int64),
+    ]
+
+
+class CsaGatherKvArgs(ctypes.Structure):
+    """Mirror of ``csa_gather_kv_args_t`` (the arguments of csa_gather_kv, for csa_run_batch)."""
+
+    _fields_ = [
+        ("k", c_void_p),
+        ("v", c_void_p),
+        ("ld_bytes", c_int64),
+        ("group_rows", c_int32),
+        ("n_groups", c_int32),
+        ("s_idx", c_void_p),
+        ("s_count", c_void_p),
+        ("max_rows", c_int32),
+        ("_pad0", c_int32),
+        ("k_out", c_void_p),
+        ("v_out", c_void_p),
+        ("out_ld_bytes", c_int64),
+        ("out_group_rows", c_int32),
+        ("row_bytes", c_int32),
+    ]
+
+
+class CsaPeerSignalArgs(ctypes.Structure):
+    """Mirror of ``csa_peer_signal_args_t``."""
+
+    _fields_ = [
+        ("done", c_void_p * CSA_MAX_PEERS),
+        ("n_peers", c_int32),
+        ("self_", c_int32),
+        ("epoch", c_uint32),
+        ("_pad0", c_uint32),
+    ]
+
+
+class CsaCall(ctypes.Structure):
+    """Mirror of ``csa_call_t``."""
+
+    _fields_ = [("kind", c_int32), ("_pad0", c_int32), ("args", c_void_p)]
+
+
+CSA_CALL_LINEAR, CSA_CALL_ATTN, CSA_CALL_GATHER_KV, CSA_CALL_PEER_SCATTER, CSA_CALL_PEER_SIGNAL, \
+    CSA_CALL_EVENT_RECORD = 1, 2, 3, 4, 5, 6
+
 CSA_ATTN_NO_SPLIT = 1
 CSA_ATTN_B_FIRST = 2
 
@@ -147,7 +212,8 @@ _lib: Optional[ctypes.CDLL] = None
 # Launch accounting (how many of OUR kernels were launched, by entry point) and optional CUDA-event timing of the
 # attention launches on the launching stream; both are read by bench.py.
 LAUNCHES = {"csa_attn_fwd": 0, "csa_compact_rows": 0, "csa_validate_mask": 0, "csa_gather_rows": 0,
-            "csa_sample_ranges": 0, "csa_gather_kv": 0, "csa_peer_scatter_kv": 0, "csa_peer_signal": 0}
+            "csa_sample_ranges": 0, "csa_gather_kv": 0, "csa_peer_scatter_kv": 0, "csa_peer_signal": 0,
+            "csa_linear": 0}
 ATTN_EVENTS: Optional[list] = None   # when a list: (start_event, end_event, n_groups, n_frames, n_q, heads) appended
 
 
@@ -212,6 +278,10 @@ def load() -> ctypes.CDLL:
     lib.csa_ipc_open.argtypes = [c_void_p, POINTER(c_void_p)]
     lib.csa_ipc_close.restype = c_int32
     lib.csa_ipc_close.argtypes = [c_void_p]
+    lib.csa_linear.restype = c_int32
+    lib.csa_linear.argtypes = [POINTER(CsaLinearArgs), c_void_p]
+    lib.csa_run_batch.restype = c_int32
+    lib.csa_run_batch.argtypes = [POINTER(CsaCall), c_int32, c_void_p, POINTER(c_int32)]
 
     v = lib.csa_abi_version()
     if v != CSA_ABI_VERSION:
@@ -269,6 +339,123 @@ def dtype_code(dt: torch.dtype) -> int:
     raise CsaNativeError(f"consistent self-attention kernels support fp16/bf16 only, got {dt}")
 
 
+# ---------------------------------------------------------------------------------------------- batched issue
+# A processor call is a fixed sequence of launches (projections, K/V gather or peer exchange, attention, output
+# projection).  Between begin_batch() and flush_batch() the wrappers below that are batchable only BUILD their
+# argument blocks; flush_batch() hands the whole sequence to csa_run_batch — one transition into the library per
+# processor call.  Nothing else may be enqueued on the stream in between (torch kernels would overtake the batch):
+# code that has to do so calls flush_batch() first.
+_BATCH: Optional[list] = None
+_BATCH_STREAM: int = 0
+_BATCH_NAMES = {CSA_CALL_LINEAR: "csa_linear", CSA_CALL_ATTN: "csa_attn_fwd", CSA_CALL_GATHER_KV: "csa_gather_kv",
+                CSA_CALL_PEER_SCATTER: "csa_peer_scatter_kv", CSA_CALL_PEER_SIGNAL: "csa_peer_signal",
+                CSA_CALL_EVENT_RECORD: "cudaEventRecord"}
+
+
+def begin_batch(like: torch.Tensor) -> None:
+    global _BATCH, _BATCH_STREAM
+    if _BATCH is not None:
+        flush_batch()
+    _BATCH = []
+    _BATCH_STREAM = _stream_ptr(like)
+
+
+def flush_batch() -> None:
+    """Issue what has been collected (no-op when no batch is open) and close the batch."""
+    global _BATCH
+    calls, _BATCH = _BATCH, None
+    if not calls:
+        return
+    n = len(calls)
+    arr = (CsaCall * n)()
+    for i, (kind, a) in enumerate(calls):
+        arr[i].kind = kind
+        arr[i].args = a if isinstance(a, int) else ctypes.addressof(a)
+    failed = c_int32(-1)
+    rc = load().csa_run_batch(arr, n, _BATCH_STREAM, ctypes.byref(failed))
+    if rc != 0:
+        what = _BATCH_NAMES.get(calls[failed.value][0], "?") if 0 <= failed.value < n else "csa_run_batch"
+        _check(rc, f"{what} (entry {failed.value} of a batch of {n})")
+
+
+def abort_batch() -> None:
+    """Drop an open batch without issuing it (error paths)."""
+    global _BATCH
+    _BATCH = None
+
+
+def _issue(kind: int, a, direct, what: str, stream: int) -> None:
+    """Launch now, or defer into the open batch (same stream only)."""
+    if _BATCH is not None and stream == _BATCH_STREAM:
+        _BATCH.append((kind, a))
+    else:
+        _check(direct(stream), what)
+
+
+_EVENT_POOL: list = []
+
+
+def _pooled_event() -> "torch.cuda.Event":
+    """A timing event whose cudaEvent_t exists (torch creates it lazily at the first record)."""
+    if _EVENT_POOL:
+        return _EVENT_POOL.pop()
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def prepare_event_pool(n: int) -> None:
+    while len(_EVENT_POOL) < n:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        _EVENT_POOL.append(e)
+
+
+_LINEAR_WS: dict = {}
+
+
+def _linear_workspace(device: torch.device) -> torch.Tensor:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    ws = _LINEAR_WS.get(idx)
+    if ws is None:
+        ws = _LINEAR_WS[idx] = torch.empty(32 << 20, dtype=torch.uint8, device=device)
+    return ws
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[M, N] = x[M, K] @ w[N, K].T (+ bias)`` (see csa_linear): nn.Linear's layouts, 16-bit in/out, fp32
+    accumulation.  2-D operands with unit column stride; batchable."""
+    _require_cuda(x, w)
+    ensure_device(x.device)
+    if x.dim() != 2 or w.dim() != 2 or x.stride(1) != 1 or w.stride(1) != 1 or x.shape[1] != w.shape[1] or \
+            w.dtype != x.dtype:
+        raise CsaNativeError("linear expects 2-D x (M, K) and w (N, K) of one 16-bit dtype, unit column stride")
+    m, k = x.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty((m, n), dtype=x.dtype, device=x.device)
+    elif out.shape != (m, n) or out.stride(1) != 1 or out.dtype != x.dtype:
+        raise CsaNativeError("linear: out must be (M, N) of x's dtype with unit column stride")
+    a = CsaLinearArgs()
+    a.struct_size = ctypes.sizeof(CsaLinearArgs)
+    a.dtype = dtype_code(x.dtype)
+    a.m, a.n, a.k = m, n, k
+    a.x, a.ldx = x.data_ptr(), x.stride(0)
+    a.w, a.ldw = w.data_ptr(), w.stride(0)
+    if bias is not None:
+        if bias.dtype != x.dtype or bias.numel() != n or not bias.is_contiguous():
+            raise CsaNativeError("linear: bias must be a contiguous (N,) tensor of x's dtype")
+        a.bias = bias.data_ptr()
+    a.y, a.ldy = out.data_ptr(), out.stride(0)
+    ws = _linear_workspace(x.device)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    lib = load()
+    _issue(CSA_CALL_LINEAR, a, lambda st: lib.csa_linear(ctypes.byref(a), st), "csa_linear", _stream_ptr(x))
+    LAUNCHES["csa_linear"] += 1
+    return out
+
+
 def idx_stride_for(n_cols: int) -> int:
     return (n_cols + CSA_TILE - 1) // CSA_TILE * CSA_TILE
 
@@ -281,6 +468,7 @@ def compact_rows(mask_rows: torch.Tensor, n_rows: int, n_cols: int, row_stride: 
     ``mask_rows`` is a bool/uint8 CUDA tensor whose first element is row 0, column 0; rows are ``row_stride``
     bytes apart (0 = the same vector for every row).  Returns ``(idx [n_rows, stride] int32, counts [n_rows])``.
     """
+    flush_batch()   # launches immediately: whatever was deferred before it goes first
     _require_cuda(mask_rows)
     ensure_device(mask_rows.device)
     if mask_rows.dtype not in (torch.bool, torch.uint8):
@@ -299,6 +487,7 @@ def compact_rows(mask_rows: torch.Tensor, n_rows: int, n_cols: int, row_stride: 
 
 def validate_mask(mask: torch.Tensor, block_n: int) -> torch.Tensor:
     """Returns a device int32 scalar: number of 16-byte words that differ from their block's first row."""
+    flush_batch()   # launches immediately: whatever was deferred before it goes first
     _require_cuda(mask)
     ensure_device(mask.device)
     if mask.dim() != 2 or mask.stride(1) != 1:
@@ -315,6 +504,7 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, max_rows: int, row_base: i
                 count: Optional[torch.Tensor] = None, count_adjust: int = 0,
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[i] = src[row_base + idx[i]] for i < min(count + adjust, max_rows).  src is 2-D, rows contiguous."""
+    flush_batch()   # launches immediately: whatever was deferred before it goes first
     _require_cuda(src, idx)
     ensure_device(src.device)
     if src.dim() != 2 or src.stride(1) != 1:
@@ -332,6 +522,7 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, max_rows: int, row_base: i
 
 def sample_ranges(s_idx: torch.Tensor, s_count: torch.Tensor, block_n: int, n_frames: int) -> torch.Tensor:
     """ranges [(n_frames+1), 4] int32 (see csa_sample_ranges): the runs of the sampled list each frame attends."""
+    flush_batch()   # launches immediately: whatever was deferred before it goes first
     _require_cuda(s_idx, s_count)
     ensure_device(s_idx.device)
     ranges = torch.empty((n_frames + 1, 4), dtype=torch.int32, device=s_idx.device)
@@ -354,10 +545,17 @@ def gather_kv(k: torch.Tensor, v: torch.Tensor, group_rows: int, n_groups: int, 
     out_group_rows = max_rows + CSA_TILE
     k_s = torch.empty((n_groups * out_group_rows, k.shape[1]), dtype=k.dtype, device=k.device)
     v_s = torch.empty_like(k_s)
-    rc = load().csa_gather_kv(k.data_ptr(), v.data_ptr(), k.stride(0) * es, group_rows, n_groups, s_idx.data_ptr(),
-                              s_count.data_ptr(), max_rows, k_s.data_ptr(), v_s.data_ptr(), k_s.stride(0) * es,
-                              out_group_rows, k.shape[1] * es, _stream_ptr(k))
-    _check(rc, "csa_gather_kv")
+    a = CsaGatherKvArgs()
+    a.k, a.v, a.ld_bytes = k.data_ptr(), v.data_ptr(), k.stride(0) * es
+    a.group_rows, a.n_groups = group_rows, n_groups
+    a.s_idx, a.s_count, a.max_rows = s_idx.data_ptr(), s_count.data_ptr(), max_rows
+    a.k_out, a.v_out, a.out_ld_bytes = k_s.data_ptr(), v_s.data_ptr(), k_s.stride(0) * es
+    a.out_group_rows, a.row_bytes = out_group_rows, k.shape[1] * es
+    lib = load()
+    _issue(CSA_CALL_GATHER_KV, a,
+           lambda st: lib.csa_gather_kv(a.k, a.v, a.ld_bytes, a.group_rows, a.n_groups, a.s_idx, a.s_count, a.max_rows,
+                                        a.k_out, a.v_out, a.out_ld_bytes, a.out_group_rows, a.row_bytes, st),
+           "csa_gather_kv", _stream_ptr(k))
     LAUNCHES["csa_gather_kv"] += 1
     return k_s, v_s, out_group_rows
 
@@ -453,15 +651,22 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
         if ranges.dtype != torch.int32 or not ranges.is_contiguous() or ranges.shape[-1] != 4:
             raise CsaNativeError("ranges must be a contiguous int32 tensor of shape (lists, 4)")
         a.ranges, a.range_base, a.range_step = ranges.data_ptr(), range_base, range_step
+    lib = load()
+    direct = lambda st: lib.csa_attn_fwd(ctypes.byref(a), st)   # noqa: E731
     if ATTN_EVENTS is not None:
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _check(load().csa_attn_fwd(ctypes.byref(a), stream), "csa_attn_fwd")
-        e1.record()
+        # kernel time of the attention launches on the launching stream (bench.py's roofline line)
+        e0, e1 = _pooled_event(), _pooled_event()
+        if _BATCH is not None and stream == _BATCH_STREAM:
+            _BATCH.append((CSA_CALL_EVENT_RECORD, e0.cuda_event))
+            _BATCH.append((CSA_CALL_ATTN, a))
+            _BATCH.append((CSA_CALL_EVENT_RECORD, e1.cuda_event))
+        else:
+            e0.record()
+            _check(direct(stream), "csa_attn_fwd")
+            e1.record()
         ATTN_EVENTS.append((e0, e1, n_groups, n_frames, n_q, heads))
     else:
-        _check(load().csa_attn_fwd(ctypes.byref(a), stream), "csa_attn_fwd")
+        _issue(CSA_CALL_ATTN, a, direct, "csa_attn_fwd", stream)
     LAUNCHES["csa_attn_fwd"] += 1
     return o
 
@@ -503,7 +708,9 @@ def peer_scatter_kv(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, count: 
     a.done, a.counter = done.data_ptr(), counter.data_ptr()
     if ranges is not None:
         a.ranges, a.frames_per_peer, a.idx_adjust = ranges.data_ptr(), frames_per_peer, idx_adjust
-    _check(load().csa_peer_scatter_kv(ctypes.byref(a), _stream_ptr(k)), "csa_peer_scatter_kv")
+    lib = load()
+    _issue(CSA_CALL_PEER_SCATTER, a, lambda st: lib.csa_peer_scatter_kv(ctypes.byref(a), st), "csa_peer_scatter_kv",
+           _stream_ptr(k))
     LAUNCHES["csa_peer_scatter_kv"] += 1
 
 
@@ -511,8 +718,14 @@ def peer_signal(done, self_index: int, epoch: int, like: torch.Tensor) -> None:
     """done[r][self_index] = epoch on every other GPU r, ordered after everything enqueued so far on the current
     stream of ``like``'s device (see csa_peer_signal)."""
     n = len(done)
-    arr = (c_void_p * n)(*[t.data_ptr() for t in done])
-    _check(load().csa_peer_signal(arr, n, self_index, epoch, _stream_ptr(like)), "csa_peer_signal")
+    a = CsaPeerSignalArgs()
+    for r, t in enumerate(done):
+        a.done[r] = t.data_ptr()
+    a.n_peers, a.self_, a.epoch = n, self_index, epoch
+    lib = load()
+    _issue(CSA_CALL_PEER_SIGNAL, a,
+           lambda st: lib.csa_peer_signal(ctypes.cast(a.done, POINTER(c_void_p)), n, self_index, epoch, st),
+           "csa_peer_signal", _stream_ptr(like))
     LAUNCHES["csa_peer_signal"] += 1
 
 

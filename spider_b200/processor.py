@@ -71,6 +71,10 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
     validate_masks = True
     kv_gather = "pre"       # "pre": sampled K/V rows gathered once per layer (csa_gather_kv) and streamed as plain
                             # TMA tiles; "inline": per-frame index lists, TMA gather4 inside the attention kernel
+    native_projections = True   # to_q / to_k|to_v (one GEMM) / to_out[0] issued by the library
+                            # (csa_linear) and the whole call handed over in one batch (csa_run_batch) whenever the
+                            # attn module is the plain SDXL attn1 shape (bias-free Linear q/k/v, Linear + Dropout(0)
+                            # out, no norms); anything else goes through the module's own projections
     batched_read = False    # opt-in: a read call may carry R generated frames (batch 2*R, [uncond R,
                             # cond R]); each attends bank + itself exactly like a batch-2 call, in ONE launch.  The
                             # reference generates them one pipe() call at a time (Comic_Generation.py:445-448), so a
@@ -169,10 +173,69 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
 
         # projections (the reference's to_q/to_k/to_v calls, :155,164-165 / :230,237-238); K/V of the current
         # input are needed by every branch
-        q = attn.to_q(x).view(B * N, C)
-        k = attn.to_k(x).view(B * N, C)
-        v = attn.to_v(x).view(B * N, C)
+        plan = self._native_plan(attn, x) if self.native_projections else None
+        use_native = plan is not None
+        if use_native:
+            # from here to flush_batch() the library calls are only collected; they are issued in one go
+            native.begin_batch(x)
+            try:
+                x2 = x.view(B * N, C)
+                q = native.linear(x2, plan[1])
+                kv = native.linear(x2, plan[2])       # K and V in one GEMM: columns [0, C) and [C, 2C)
+                k, v = kv[:, :C], kv[:, C:]
+            except Exception:
+                native.abort_batch()
+                raise
+        else:
+            q = attn.to_q(x).view(B * N, C)
+            k = attn.to_k(x).view(B * N, C)
+            v = attn.to_v(x).view(B * N, C)
+        try:
+            return self._attend_and_project(attn, h, hidden_states, residual, input_ndim, q, k, v, B, N, C, heads,
+                                            write, cur_step, plan)
+        except Exception:
+            native.abort_batch()
+            raise
 
+    def _native_plan(self, attn, x):
+        """``(key, w_q, w_kv, w_out, b_out)`` when the attn module is the plain SDXL attn1 shape — bias-free Linear
+        q/k/v, ``[Linear, Dropout]`` output with the dropout inactive, weights of x's dtype on x's device — else
+        None (the module's own projections are used).  ``w_kv = cat(to_k.weight, to_v.weight)``.  Cached per attn
+        module and re-validated cheaply: the weights' storage and version counters."""
+        lin = torch.nn.Linear
+        if not x.is_cuda:
+            return None
+        mods = attn._modules
+        tq, tk, tv, out = mods.get("to_q"), mods.get("to_k"), mods.get("to_v"), mods.get("to_out")
+        if type(tq) is not lin or type(tk) is not lin or type(tv) is not lin or out is None:
+            return None
+        om = out._modules
+        o0, o1 = om.get("0"), om.get("1")
+        if len(om) != 2 or type(o0) is not lin or type(o1) is not torch.nn.Dropout:
+            return None
+        wq, wk, wv, wo, bo = tq.weight, tk.weight, tv.weight, o0.weight, o0.bias
+        key = (id(attn), x.dtype, x.device, wq.data_ptr(), wq._version, wk.data_ptr(), wk._version, wv.data_ptr(),
+               wv._version, wo.data_ptr(), wo._version, None if bo is None else bo.data_ptr(),
+               o1.p != 0.0 and o1.training)
+        hit = self.__dict__.get("_nplan")
+        if hit is not None and hit[0] == key:
+            return hit if hit[1] is not None else None
+        ok = (tq.bias is None and tk.bias is None and tv.bias is None and not key[-1]
+              and all(w.dtype == x.dtype and w.device == x.device and w.is_contiguous() for w in (wq, wk, wv, wo))
+              and (bo is None or (bo.dtype == x.dtype and bo.is_contiguous())))
+        if ok:
+            native.flush_batch()     # torch.cat launches a kernel: nothing deferred may be overtaken
+            hit = (key, wq.detach(), torch.cat([wk.detach(), wv.detach()], dim=0).contiguous(), wo.detach(),
+                   None if bo is None else bo.detach())
+        else:
+            hit = (key, None, None, None, None)
+        self.__dict__["_nplan"] = hit
+        return hit if ok else None
+
+    def _attend_and_project(self, attn, h, hidden_states, residual, input_ndim, q, k, v, B, N, C, heads, write,
+                            cur_step, plan):
+        Fl = self.id_length
+        use_native = plan is not None
         entry: Optional[BankEntry] = None
         if write:
             # :87-89 — keep what the read passes need.  K/V are this call's projection outputs (zero-copy).
@@ -220,10 +283,15 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                 self._attn_standard(q, k, v, o, B, N, heads)    # :118 — bank ignored even when reading
         self._last_branch = branch
 
-        out = o.view(B, N, C)
-        out = attn.to_out[0](out)                               # :185 / :256
-        out = attn.to_out[1](out)
+        if use_native:
+            out = native.linear(o, plan[3], plan[4]).view(B, N, C)   # :185 / :256
+            native.flush_batch()                                # everything collected since the projections: ONE call
+        else:
+            out = o.view(B, N, C)
+            out = attn.to_out[0](out)                           # :185 / :256
+            out = attn.to_out[1](out)
         if input_ndim == 4:
+            b4, c4, h4, w4 = residual.shape
             out = out.transpose(-1, -2).reshape(b4, c4, h4, w4)
         if attn.residual_connection:
             out = out + residual
@@ -273,6 +341,7 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
         projection source B; nothing is concatenated."""
         Fl = self.id_length
         R = q.shape[0] // (2 * N)          # generated frames in this call (1 unless batched_read)
+        native.flush_batch()               # entry.kv() may project bank rows with torch: nothing deferred before it
         kb, vb = entry.kv(attn, device=q.device)
         if kb.shape[0] != 2 * Fl * N or kb.shape[1] != q.shape[1]:
             raise ValueError(f"id_bank entry has K/V of shape {tuple(kb.shape)}, expected {(2 * Fl * N, q.shape[1])}")

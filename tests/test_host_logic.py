@@ -276,3 +276,65 @@ def test_processor_is_deepcopy_and_module_safe():
     a.set_processor(q)
     a.to(torch.float16)
     assert a.processor is q and list(q.parameters()) == []
+
+
+# ------------------------------------------------------------------------------------------ batched issue (8f.4)
+class _FakeLib:
+    """Records what reaches the library: direct entry points and the contents of csa_run_batch."""
+
+    def __init__(self):
+        self.log = []
+
+    def csa_run_batch(self, arr, n, stream, failed):
+        self.log.append(("batch", [arr[i].kind for i in range(n)], stream))
+        return 0
+
+    def csa_linear(self, a, stream):
+        self.log.append(("linear", stream))
+        return 0
+
+    def csa_gather_rows(self, *a):
+        self.log.append(("gather_rows",))
+        return 0
+
+    def csa_last_error(self):
+        return b""
+
+
+def test_batch_defers_in_order_and_flushes_before_immediate_calls(monkeypatch):
+    lib = _FakeLib()
+    monkeypatch.setattr(native, "load", lambda: lib)
+    monkeypatch.setattr(native, "_stream_ptr", lambda t: 7)
+    monkeypatch.setattr(native, "_require_cuda", lambda *a: None)
+    monkeypatch.setattr(native, "ensure_device", lambda d: None)
+    monkeypatch.setattr(native, "_linear_workspace", lambda d: torch.zeros(64, dtype=torch.uint8))
+    x = torch.zeros((8, 16), dtype=torch.bfloat16)
+    w = torch.zeros((32, 16), dtype=torch.bfloat16)
+    # no batch open: immediate
+    native.linear(x, w)
+    assert lib.log == [("linear", 7)]
+    lib.log.clear()
+    # open batch: nothing reaches the library until the flush, then everything in order in ONE call
+    native.begin_batch(x)
+    y = native.linear(x, w)
+    native.linear(y, torch.zeros((16, 32), dtype=torch.bfloat16), torch.zeros(16, dtype=torch.bfloat16))
+    assert lib.log == []
+    native.flush_batch()
+    assert lib.log == [("batch", [native.CSA_CALL_LINEAR, native.CSA_CALL_LINEAR], 7)]
+    native.flush_batch()                      # closed: no-op
+    assert len(lib.log) == 1
+    lib.log.clear()
+    # a wrapper that launches immediately flushes what was deferred first and closes the batch
+    native.begin_batch(x)
+    native.linear(x, w)
+    idx = torch.zeros(4, dtype=torch.int32)
+    native.gather_rows(x, idx, 4)
+    native.linear(x, w)                        # after the flush: immediate again
+    assert lib.log == [("batch", [native.CSA_CALL_LINEAR], 7), ("gather_rows",), ("linear", 7)]
+    lib.log.clear()
+    # error paths drop the batch
+    native.begin_batch(x)
+    native.linear(x, w)
+    native.abort_batch()
+    native.flush_batch()
+    assert lib.log == []
