@@ -373,11 +373,14 @@ def run_b200_arm(args):
         ms_total, attn_ms = float(t[0]), float(t[1])
         if e2e:
             e2e["ms"] = float(t[2])
-        lt = torch.tensor([sum(launches.values())], device=dev, dtype=torch.int64)
+        lt = torch.tensor([sum(v for k, v in launches.items() if k != "csa_linear"), launches.get("csa_linear", 0)],
+                          device=dev, dtype=torch.int64)
         dist.all_reduce(lt)
-        total_launches = int(lt[0])
+        total_launches, gemm_launches = int(lt[0]), int(lt[1])
     else:
-        total_launches = sum(launches.values())
+        # our own kernels; the projections are cuBLASLt GEMMs issued through csa_linear and counted separately
+        total_launches = sum(v for k, v in launches.items() if k != "csa_linear")
+        gemm_launches = launches.get("csa_linear", 0)
 
     if rank == 0:
         ms_step = ms_total / args.steps
@@ -392,6 +395,7 @@ def run_b200_arm(args):
             "config": workload_config(args, world),
             "tflop_per_step": round(flops_total / args.steps / 1e12, 4),
             "gpu_launches": total_launches,
+            "library_gemm_launches": gemm_launches,
             "launches_by_entry": launches,
             "host_issue_ms_per_step": round(host_issue_ms / args.steps, 3),
             "clocks": clocks,
