@@ -263,11 +263,12 @@ class FrameSharding:
         pl = self.plan(cm, q.device)
         if self.gc > 1 and self.exchange == "p2p":
             return self._attn_write_p2p(q, k, v, o, N, heads, pl, Fl)
-        pl.host()
         if self.gc == 1:
             # one CFG half per GPU: everything is local, same as the single-GPU path with one group
             k_s, v_s, cap = native.gather_kv(k, v, Fl * N, 1, pl.s_idx, pl.s_count, Fl * N)
         else:
+            pl.host()                   # slab sizes of the all-gather: one read-back per mask
+            native.flush_batch()        # torch collectives follow: nothing deferred may be overtaken
             send = torch.empty((2, pl.pad, C), dtype=k.dtype, device=k.device)
             if pl.count_me > 0:
                 native.gather_rows(k, pl.local_idx, pl.count_me, out=send[0])
