@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(256) peer_scatter_kernel(const __grid_constant
     const uint32_t prev = atomicAdd(p.counter, 1u);
     if (prev == gridDim.x - 1) {
       *p.counter = 0u;
-      __threadfence_system();
-      for (int r = 0; r < p.n_peers; ++r) st_release_sys(p.ready[r] + p.self, p.epoch);
+      __threadfence_system();   // orders every block's stores (observed through the counter) before the flags
+      for (int r = 0; r < p.n_peers; ++r) st_relaxed_sys(p.ready[r] + p.self, p.epoch);
     }
   }
 }

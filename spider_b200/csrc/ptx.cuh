@@ -230,6 +230,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// relaxed system-scope store: the release half of a flag hand-over whose ordering comes from ONE preceding
+// __threadfence_system() shared by several flag stores (a st.release each would repeat the fence)
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 #ifndef CSA_FLAG_WATCHDOG_POLLS
 #define CSA_FLAG_WATCHDOG_POLLS (1u << 25)
 #endif
