@@ -268,6 +268,15 @@ def run_b200_arm(args):
         from spider_b200.dist import FrameSharding
         sharding = FrameSharding(Fl, None, dev, exchange=args.exchange)
         units_local = sharding.local_batch
+        if args.exchange == "p2p" and sharding.gc > 1:
+            from spider_b200.dist import PeerExchangeUnavailable
+            try:   # map the peers' buffers now: a box without a peer-memory path falls back as a whole, and says so
+                sharding.prepare_peers({(n, c) for (n, c, h) in plan})
+            except PeerExchangeUnavailable as e:
+                if rank == 0:
+                    print(f"bench.py: {e} -> NCCL all-gather", file=sys.stderr, flush=True)
+                sharding.exchange = args.exchange = "nccl"
+                sharding.peers = None
 
     # identical weights / masks on every rank: same seeds (the mask sample must agree across ranks)
     torch.manual_seed(0)

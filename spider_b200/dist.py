@@ -60,6 +60,11 @@ def _import_tensor(handle, device) -> torch.Tensor:
     return pickle.loads(h).view(torch.uint8).view(-1)
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """Raised on EVERY rank of a CFG half when any of them cannot map a peer's buffers (no P2P path, CUDA IPC not
+    permitted in this container, ...)."""
+
+
 class PeerExchange:
     """Symmetric exchange buffers of one CFG half: on every rank two slots of (K[S], V[S]) byte buffers plus arrival
     (``ready``) and release (``done``) flags, each mapped into every peer (CUDA IPC + P2P access).  Layer calls are
@@ -98,13 +103,26 @@ class PeerExchange:
                                group=sh.half_group)
         me = sh.rank_in_half
         self._keep = (local, flags)                # the peers' mappings alias these allocations
-        self.bufs, self.flags = [], []
-        for r, (hb, hf, ep) in enumerate(handles):
-            if ep != self.epoch:
-                raise RuntimeError("ranks diverged: peer exchange epochs differ (not every rank made the same calls)")
-            b, f = (local, flags) if r == me else (_import_tensor(hb, self.device), _import_tensor(hf, self.device))
-            self.bufs.append(b)
-            self.flags.append(f.view(torch.int32).view(3, native.CSA_MAX_PEERS))
+        bufs, flag_views, err = [], [], None
+        try:
+            for r, (hb, hf, ep) in enumerate(handles):
+                if ep != self.epoch:
+                    raise RuntimeError("ranks diverged: peer exchange epochs differ (not every rank made the same "
+                                       "calls)")
+                b, f = (local, flags) if r == me else (_import_tensor(hb, self.device), _import_tensor(hf, self.device))
+                bufs.append(b)
+                flag_views.append(f.view(torch.int32).view(3, native.CSA_MAX_PEERS))
+        except Exception as e:   # noqa: BLE001 - reported to every rank below, then raised everywhere
+            err = f"rank {sh.rank}: {type(e).__name__}: {e}"
+        # every rank learns whether every rank could map every buffer: either all go on or all raise (a rank that
+        # raised alone would leave the others waiting in the next collective)
+        errs = [None] * sh.gc
+        dist.all_gather_object(errs, err, group=sh.half_group)
+        failed = [e for e in errs if e]
+        if failed:
+            raise PeerExchangeUnavailable("peer-memory exchange could not be set up (" + "; ".join(failed) + "); "
+                                          "use FrameSharding(exchange='nccl')")
+        self.bufs, self.flags = bufs, flag_views
         self.cap_bytes = cap
         self._views = {}
         self._ready = [f[0] for f in self.flags]
@@ -284,6 +302,15 @@ class FrameSharding:
                         k_a=k_s, v_a=v_s, a_group_rows=cap, ranges=pl.ranges, range_base=self.f0, range_step=1,
                         k_b=k, v_b=v, b_group_rows=fr * N, cb=(0, N, N))
         return o
+
+    def prepare_peers(self, layers, element_size: int = 2) -> None:
+        """Collective over the CFG half: allocate and map the exchange buffers up front for the given layer shapes
+        (iterable of ``(tokens per frame, channels)``).  Raises ``PeerExchangeUnavailable`` on every rank of the half
+        if any of them cannot map its peers."""
+        if self.gc > 1 and self.exchange == "p2p":
+            if self.peers is None:
+                self.peers = PeerExchange(self, self.device)
+            self.peers.ensure(max((self.id_length * n + native.CSA_TILE) * c * element_size for (n, c) in layers))
 
     def _attn_write_p2p(self, q, k, v, o, N, heads, pl: ShardPlan, Fl):
         """Fused exchange: this rank's sampled rows go straight into every peer's S-ordered K[S], V[S] buffer

@@ -221,3 +221,44 @@ def test_sharding_geometry_errors():
         assert (sh.gc, sh.cfg, sh.frames_local, sh.f0, sh.half_group) == (1, 1, 4, 0, None)
     finally:
         sd.dist = real
+
+
+def _worker_unavailable(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    mp.set_sharing_strategy("file_system")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import spider_b200.dist as sd
+        if rank == 1:     # one rank of the unconditional half cannot map its peer
+            def broken(handle, device):
+                raise OSError("peer mapping refused")
+            sd._import_tensor = broken
+        sh = sd.FrameSharding(FL, None, torch.device("cpu"), exchange="p2p")
+        try:
+            sh.prepare_peers([(16, C), (64, C)], element_size=4)
+            q.put((rank, "ok", sh.peers.allocations))
+        except sd.PeerExchangeUnavailable as e:
+            q.put((rank, "unavailable", str(e)))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_failure_is_seen_by_the_whole_half():
+    """A rank that cannot map a peer's buffers must not leave its peers waiting: every rank of that CFG half raises
+    PeerExchangeUnavailable (and the other half, which is independent, goes on)."""
+    world = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_unavailable, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    results = dict((r[0], r[1:]) for r in [q.get(timeout=240) for _ in range(world)])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0][0] == results[1][0] == "unavailable" and "rank 1" in results[0][1]
+    assert results[2] == ("ok", 1) and results[3] == ("ok", 1)
