@@ -32,9 +32,11 @@
 #define CSA_PINGPONG 1
 #endif
 // The token is handed over after this 32-key chunk (0..3) of the exp phase has been issued: 3 = strict alternation,
-// smaller = the two exp phases overlap at the seam, which keeps the MUFU queue full across the hand-over.
+// smaller = the two exp phases overlap, which puts two warps on the sub-partition's MUFU at once (a single warp
+// cannot keep it busy: it issues nothing else while its own MUFU instruction is dispatched).  Measured
+// (profiles/r01f_token_chunk_sweep.log, step-equivalent TFLOP/s): 0 -> 715, 1 -> 769, 2 -> 747, 3 -> 736.
 #ifndef CSA_TOKEN_CHUNK
-#define CSA_TOKEN_CHUNK 2
+#define CSA_TOKEN_CHUNK 1
 #endif
 // Organisations that were built, measured slower on B200 and removed ("what did not work"):
 // two threads per score row (row max exchanged through shared memory), software-pipelined score loads inside the exp
