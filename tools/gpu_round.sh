@@ -39,6 +39,11 @@ for w in $WHAT; do
         --log-file "$OUT/launches.csv" python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > "$OUT/launches.log" 2>&1
       echo "ncu launches exit $?"
       ;;
+    sdpa)
+      # same-box GPU comparator: the reference call through torch SDPA with the dense mask
+      timeout 600 python tools/bench_torch_sdpa.py > "$OUT/torch_sdpa.json" 2> "$OUT/torch_sdpa.err"
+      echo "torch sdpa exit $?"; cat "$OUT/torch_sdpa.json"
+      ;;
     full)
       # one 32x32-class and one 64x64-class attention launch of a warm step
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:csa_attn_kernel -s 136 -c 4 \
