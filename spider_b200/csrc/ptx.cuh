@@ -209,6 +209,24 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 
+// 16-column load (rare paths that must stay small in registers)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// 8 columns variant (16 keys of 16-bit P values)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+
 // 16 columns variant (one 32-key chunk of 16-bit P values)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -284,6 +302,12 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return r;
 }
 
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 // exp2 on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial, max relative error 8.6e-5 —
 // far below the 2^-9 rounding of the 16-bit P it feeds).  Two elements at a time with packed fp32 ops.  Offloading a
 // fraction of the exponentials from the MUFU (16 ex2/clk/SM) is what lets a head_dim-64 softmax keep up with the
@@ -315,6 +339,34 @@ __device__ __forceinline__ void poly_exp2_x2(uint64_t x2, float& p0, float& p1) 
   uint64_t q2 = ffma2(c3, f2, c2);
   q2 = ffma2(q2, f2, c1);
   q2 = ffma2(q2, f2, c0);
+  float q0, q1, t0, t1;
+  unpack_f2(q2, q0, q1);
+  unpack_f2(t2, t0, t1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
+// Clamp-free variant for the softmax inner loop: round-to-nearest range reduction with the 1.5*2^23 trick
+// (3 FADD2), minimax polynomial on [-0.5, 0.5] (degree 2: max relative error 1.73e-3, below the 2^-8 half-ulp of a
+// bf16 P; degree 3: 7.5e-5, below the 2^-11 half-ulp of an fp16 P), exponent inserted with one LEA per element.
+// The CALLER guarantees -120 <= x <= 120 (the softmax checks the tile's minimum and takes the MUFU path otherwise).
+// Measured (profiles/r02a_pipe_probe2.log): the softmax mix costs 16.4 SMSP-clk per element pair with MUFU only and
+// 13.2 with 3 of every 8 pairs through the degree-2 polynomial (4 warps per sub-partition).
+template <int DEG>
+__device__ __forceinline__ void poly_exp2_fast_x2(uint64_t x2, float& p0, float& p1) {
+  const uint64_t magic = pack_f2(12582912.0f, 12582912.0f);
+  const uint64_t t2 = fadd2(x2, magic);
+  const uint64_t n2 = fsub2(t2, magic);
+  const uint64_t f2 = fsub2(x2, n2);
+  uint64_t q2;
+  if constexpr (DEG == 2) {
+    q2 = ffma2(pack_f2(0.23842891f, 0.23842891f), f2, pack_f2(0.70344800f, 0.70344800f));
+    q2 = ffma2(q2, f2, pack_f2(1.0004431f, 1.0004431f));
+  } else {
+    q2 = ffma2(pack_f2(0.05517166f, 0.05517166f), f2, pack_f2(0.24261113f, 0.24261113f));
+    q2 = ffma2(q2, f2, pack_f2(0.69326097f, 0.69326097f));
+    q2 = ffma2(q2, f2, pack_f2(0.99992806f, 0.99992806f));
+  }
   float q0, q1, t0, t1;
   unpack_f2(q2, q0, q1);
   unpack_f2(t2, t0, t1);
