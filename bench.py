@@ -137,71 +137,130 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference
-def cpu_reference_sample(args, reps: int):
-    """Time the reference algorithm (oracle port, fp32, torch CPU with all host threads) on a bounded sample of the
-    step: ONE write-consistent call of a 32x32-class layer and ONE of a 64x64-class layer, dense (T*N)^2 mask as the
-    reference builds it, extrapolated to the step by the layer counts of the plan.  Returns a dict."""
-    from oracle import reference_port as rp          # the only place bench.py touches oracle/: the CPU baseline
-    from oracle.fake_diffusers import FakeAttention
+def _host_threads() -> int:
+    """All the host threads the CPU arm may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which would make
+    the reference arm a single-core run at N > 1: set the thread count explicitly."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
 
-    Fl = args.frames
-    H = W = args.res
-    plan = layer_plan(H, W, args.placement)
-    kinds = {}
-    for (n, c, h) in plan:
-        kinds[(n, c, h)] = kinds.get((n, c, h), 0) + 1
-    torch.manual_seed(0)
-    random.seed(0)
-    m32, m16 = rp.cal_attn_mask_xl(Fl + 1, Fl, args.sa, args.sa, H, W)
-    n32 = (H // 32) * (W // 32)
-    per_kind = {}
-    for (n, c, h), cnt in kinds.items():
-        attn = FakeAttention(c, h)
-        x = torch.randn(2 * Fl, n, c)
-        st = rp.StoryState(write=True, cur_step=25, total_count=10 ** 9, sa32=args.sa, sa64=args.sa, height=H,
-                           width=W, mask1024=m32, mask4096=m16)
-        orc = rp.ConsistentAttnOracle(st, id_length=Fl)
-        mask = m32 if n == n32 else m16
-        rows = mask[::n][:Fl, :Fl * n]
-        counts = rows.sum(dim=1).tolist()
-        best = float("inf")
-        with torch.no_grad():
-            for _ in range(reps):
-                st.cur_step = 25
+
+class CpuReference:
+    """The reference algorithm (oracle port: fp32, torch CPU, dense (T*N)^2 mask as the reference builds it) driven
+    through the same processor calls as the B200 arm: write pass, cur_step = 25, gate forced to the consistent branch.
+    One FakeAttention + one input per layer CLASS (the layers of a class cost the same)."""
+
+    def __init__(self, args):
+        from oracle import reference_port as rp          # the only place bench.py touches oracle/: the CPU baseline
+        from oracle.fake_diffusers import FakeAttention
+
+        self.rp = rp
+        self.Fl = args.frames
+        self.H = self.W = args.res
+        self.plan = layer_plan(self.H, self.W, args.placement)
+        self.threads = _host_threads()
+        torch.manual_seed(0)
+        random.seed(0)
+        m32, m16 = rp.cal_attn_mask_xl(self.Fl + 1, self.Fl, args.sa, args.sa, self.H, self.W)
+        self.state = rp.StoryState(write=True, cur_step=25, total_count=10 ** 9, sa32=args.sa, sa64=args.sa,
+                                   height=self.H, width=self.W, mask1024=m32, mask4096=m16)
+        self.n32 = (self.H // 32) * (self.W // 32)
+        self.kinds = {}
+        for kind in self.plan:
+            self.kinds[kind] = self.kinds.get(kind, 0) + 1
+        self.layers = {}
+        for (n, c, h) in self.kinds:
+            self.layers[(n, c, h)] = (FakeAttention(c, h), torch.randn(2 * self.Fl, n, c),
+                                      rp.ConsistentAttnOracle(self.state, id_length=self.Fl))
+
+    def flops(self, kinds_counts) -> float:
+        total = 0.0
+        for (n, c, h), cnt in kinds_counts.items():
+            mask = self.state.mask1024 if n == self.n32 else self.state.mask4096
+            counts = mask[::n][:self.Fl, :self.Fl * n].sum(dim=1).tolist()
+            total += cnt * attn_flops(n, h, counts)
+        return total
+
+    def run(self, kinds_counts, regen_masks: bool) -> float:
+        """Seconds for `cnt` processor calls of every layer class (+ the per-step mask re-sampling)."""
+        st = self.state
+        real_random = random.random
+        random.random = lambda: 0.999    # gate forced open (:98-103), like the B200 arm
+        try:
+            with torch.no_grad():
                 t0 = time.perf_counter()
-                orc.consistent(attn, x, None, mask[:Fl * n, :Fl * n])
-                best = min(best, time.perf_counter() - t0)
-        per_kind[(n, c, h)] = (best, attn_flops(n, h, counts), cnt)
-    t_step = sum(t * cnt for t, _, cnt in per_kind.values())
-    f_step = sum(f * cnt for _, f, cnt in per_kind.values())
-    t_sample = sum(t for t, _, _ in per_kind.values())
-    return {
-        "value": f_step / t_step / 1e12,
+                for kind, cnt in kinds_counts.items():
+                    attn, x, orc = self.layers[kind]
+                    for _ in range(cnt):
+                        st.cur_step, st.attn_count, st.write = 25, 0, True
+                        orc(attn, x)
+                if regen_masks:          # :119-125, once per denoise step
+                    st.mask1024, st.mask4096 = self.rp.cal_attn_mask_xl(self.Fl + 1, self.Fl, st.sa32, st.sa64,
+                                                                        self.H, self.W)
+                return time.perf_counter() - t0
+        finally:
+            random.random = real_random
+
+    def sample_counts(self):
+        """The step's layer mix divided by its gcd: 30 + 6 layers -> 5 + 1 (one sixth of the step, same proportions)."""
+        import math
+        g = 0
+        for cnt in self.kinds.values():
+            g = math.gcd(g, cnt)
+        return {k: cnt // g for k, cnt in self.kinds.items()}, g
+
+
+def cpu_reference_sample(args, steps: int, warmup: int, whole_step: bool):
+    """Time the reference algorithm on this box's host cores.  A *step* of this arm is a bounded sample of the
+    denoise step: the step's layer mix divided by its gcd (5 calls of the 32x32 class + 1 of the 64x64 class for the
+    36-layer placement), all host threads; TFLOP/s = the sample's algorithmic FLOPs / its time (no extrapolation),
+    ms_per_step = sample time x gcd.  With `whole_step`, one complete denoise step (all layers + mask re-sampling) is
+    run once as well and reported next to it."""
+    ref = CpuReference(args)
+    sample, g = ref.sample_counts()
+    for _ in range(warmup):
+        ref.run(sample, regen_masks=False)
+    times = [ref.run(sample, regen_masks=False) for _ in range(max(1, steps))]
+    t_sample = sum(times) / len(times)
+    f_sample = ref.flops(sample)
+    out = {
+        "value": f_sample / t_sample / 1e12,
         "unit": UNIT,
-        "cores": torch.get_num_threads(),
+        "cores": ref.threads,
         "host_cpus": os.cpu_count(),
         "kind": "port",
-        "sample": (f"one write-consistent call per layer class ({', '.join(f'N={n} C={c}' for n, c, _ in per_kind)}), "
-                   f"fp32, dense mask, best of {reps}; {t_sample:.2f} s per sample; extrapolated to the "
-                   f"{len(plan)}-layer step by layer counts ({t_step:.1f} s/step)"),
-        "ms_per_step": t_step * 1e3,
+        "sample": (f"{len(times)} timed samples (mean) of 1/{g} denoise step each = "
+                   + " + ".join(f"{cnt} x (N={n}, C={c})" for (n, c, _), cnt in sample.items())
+                   + f" write-consistent processor calls, fp32, dense mask, {ref.threads} threads; "
+                   f"{t_sample:.2f} s per sample; ms_per_step = sample x {g}"),
+        "ms_per_step": t_sample * g * 1e3,
+        "steps_timed": len(times),
     }
+    if whole_step:
+        t_whole = ref.run(ref.kinds, regen_masks=True)
+        out["whole_step_ms"] = t_whole * 1e3
+        out["whole_step_tflops"] = ref.flops(ref.kinds) / t_whole / 1e12
+        out["sample"] += (f"; one WHOLE step ({len(ref.plan)} calls + mask re-sampling) run once: "
+                          f"{t_whole:.1f} s = {out['whole_step_tflops']:.3f} TFLOP/s")
+    return out
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    reps = max(1, min(args.steps, 3))
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_sample(args, 1)
-    base = cpu_reference_sample(args, reps)
+    base = cpu_reference_sample(args, steps=args.steps, warmup=min(args.warmup, 2), whole_step=True)
+    keys = ("value", "unit", "cores", "host_cpus", "kind", "sample", "whole_step_ms", "whole_step_tflops")
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+        "steps": base["steps_timed"], "warmup": min(args.warmup, 2), "ms_per_step": base["ms_per_step"],
+        "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, n_gpus=args.gpus),
-        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample")},
+        "cpu_baseline": {k: base[k] for k in keys if k in base},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -425,7 +484,7 @@ def run_b200_arm(args):
                            "unit": UNIT, "ms_per_step": round(e2e["ms"] / args.steps, 4),
                            "h2d_bytes_per_step": e2e["h2d"] * world, "d2h_bytes_per_step": e2e["d2h"] * world}
         if world == 1 and not args.no_cpu:
-            base = cpu_reference_sample(args, 2)
+            base = cpu_reference_sample(args, steps=3, warmup=1, whole_step=False)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -16,13 +16,21 @@
 //               online softmax in the exp2 domain with lazy (threshold 8) rescaling of O, P written to TMEM as
 //               16-bit, final 1/l normalisation and store.
 // Two 128-row Q tiles are ping-ponged so that the tensor core works on one tile while the other is in softmax.
+#include <type_traits>
+
 #include "ptx.cuh"
 #include "csa_internal.h"
 
-// How many of every 16 element pairs take the polynomial exp2 (FMA/ALU pipes) instead of MUFU.EX2 (measured
-// neutral: the softmax is bound by the latency chain of a tile iteration, not by MUFU throughput alone).
+// How many of every 16 element pairs take the polynomial exp2 (FMA/ALU pipes, ptx.cuh poly_exp2_fast_x2: clamp-free,
+// degree 2 for a bf16 P, degree 3 for an fp16 P) instead of MUFU.EX2.  ptxas paces a warp's exp loop at one MUFU
+// every 8 cycles and fills the gaps (decoded stall fields: 16.1 clk per pair with or without the polynomial), so the
+// gain is small: 4/16 -> 864 vs 853 TFLOP/s on the 64x64 layer, 6/16 and more lose (profiles/r02h_classic_poly_sweep
+// .log).  Round 2 also built and measured two reorganisations that were meant to lift the MUFU wall and did not:
+// 16 softmax warps with the keys of a tile split between two warps per row (issue-bound: 475 instructions per tile
+// and warp, profiles/experiments/r02_16warp_keysplit.patch) and a lazily updated reference point that takes the row
+// max off the latency chain (the exp phase grows by what the chain loses, profiles/experiments/r02_lazy_max.patch).
 #ifndef CSA_POLY_PAIRS
-#define CSA_POLY_PAIRS 0
+#define CSA_POLY_PAIRS 4
 #endif
 // Exp-phase ping-pong: the two softmax warps that share an SM sub-partition (same TMEM lane quarter, Q tile 0 and
 // Q tile 1) hand a token back and forth through a pair of named barriers, so that one exponentiates (MUFU-bound)
@@ -70,9 +78,18 @@ struct Tracer {
 };
 #define TRACE_INIT(slot, on) Tracer tracer; tracer.init(slot, on)
 #define TRACE(id) tracer.ev(id)
+// per-CTA unit boundaries (globaltimer, ns) behind the event slots: [blockIdx.x][64] — tools/trace_ctas.py
+constexpr int kCtaMarks = 64;
+#define TRACE_CTA(on, k, tag)                                                                                  \
+  do {                                                                                                         \
+    if ((on) && g_trace != nullptr && (k) < kCtaMarks)                                                         \
+      g_trace[kTraceSlots * kTraceEvents + blockIdx.x * kCtaMarks + (k)] =                                     \
+          (static_cast<unsigned long long>(tag) << 56) | (globaltimer_ns() & 0xffffffffffffffull);             \
+  } while (0)
 #else
 #define TRACE_INIT(slot, on)
 #define TRACE(id)
+#define TRACE_CTA(on, k, tag)
 #endif
 
 constexpr int kBM = 128;  // query rows per Q tile
@@ -91,10 +108,11 @@ constexpr uint32_t kColS = 0;    // S0 at 0, S1 at 128
 constexpr uint32_t kColO = 256;  // O0 at 256, O1 at 320
 constexpr uint32_t kColP = 384;  // P0 at 384, P1 at 448 (128 16-bit values = 64 columns)
 
-// pair i of a 16-pair chunk goes to the polynomial iff it is one of CSA_POLY_PAIRS evenly spread slots
-__host__ __device__ constexpr bool poly_pair(int i) {
-  return ((i + 1) * CSA_POLY_PAIRS) / 16 != (i * CSA_POLY_PAIRS) / 16;
-}
+// pair i of a 16-pair chunk goes to the polynomial iff it is one of `n` evenly spread slots
+__host__ __device__ constexpr bool poly_pair(int i, int n) { return ((i + 1) * n) / 16 != (i * n) / 16; }
+#ifndef CSA_POLY_PAIRS_F16
+#define CSA_POLY_PAIRS_F16 CSA_POLY_PAIRS
+#endif
 
 struct __align__(1024) AttnSmem {
   uint8_t q[2][kTileBytes];
@@ -572,6 +590,12 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
     bool have_token = (s == 0);
 #endif
     TRACE_INIT(s, (warp & 3) == 0 && lane == 0);
+#if CSA_TRACE
+    const bool cta_mark = warp == 4 && lane == 0;
+    int n_mark = 0;
+    TRACE_CTA(cta_mark, n_mark, 1);
+    ++n_mark;
+#endif
 
     if (lane == 0) mbar_arrive(bar_f);  // S is free before the first QK of the kernel
 
@@ -595,6 +619,8 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       walk.init(w);
       for (int t = 0; t < w.t0; ++t) walk.next();
       uint32_t sv[4][32];  // the score row of the current tile (a thread owns a whole 128-key row)
+      constexpr int kPoly = kBF16 ? CSA_POLY_PAIRS : CSA_POLY_PAIRS_F16;
+      constexpr int kDeg = kBF16 ? 2 : 3;
 
       for (int j = 0; j < nt; ++j) {
         TRACE(1);
@@ -625,11 +651,15 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         float mx[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+        float mn = INFINITY;  // minimum over the pairs that would take the polynomial (guards its exponent arithmetic)
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; i += 2)
+          for (int i = 0; i < 32; i += 2) {
             mx[(i >> 1) & 7] = fmax3(mx[(i >> 1) & 7], __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+            if (kPoly > 0 && poly_pair(i >> 1, kPoly))
+              mn = fmin3(mn, __uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1]));
+          }
         const float m_new =
             fmaxf(m, fmax3(fmax3(mx[0], mx[1], mx[2]), fmax3(mx[3], mx[4], mx[5]), fmaxf(mx[6], mx[7])) * sc);
 #if CSA_TRACE
@@ -663,9 +693,12 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
 
         TRACE(5);
 
-        // P = exp2(S*scale - m) in chunks of 32 keys: FFMA2 -> MUFU.EX2 -> FADD2 row sum -> pack -> TMEM
+        // P = exp2(S*scale - m) in chunks of 32 keys: FFMA2 -> MUFU.EX2 | polynomial -> FADD2 row sum -> pack -> TMEM.
+        // The polynomial has no clamp: its arguments must stay above -120 (x <= 8 holds by construction); the tile's
+        // minimum over its pairs decides — a ragged (-inf padded) or extreme tile takes the MUFU for every pair.
         uint64_t nm2 = pack_f2(-m, -m);
         uint64_t ls[2] = {0ull, 0ull};
+        const bool poly_ok = kPoly > 0 && __all_sync(0xffffffffu, fmaf(mn, sc, -m) >= -120.0f);
 #if CSA_PINGPONG
         if (have_token) {
           have_token = false;
@@ -675,31 +708,39 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         asm volatile("" : "+l"(nm2));  // every exponential depends on nm2: none may be hoisted above the token
 #endif
         TRACE(6);
+        auto exp_pass = [&](auto use_poly) {
+          constexpr bool kUsePoly = decltype(use_poly)::value;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint64_t xs[16];
+          for (int c = 0; c < 4; ++c) {
+            uint64_t xs[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            xs[i] = ffma2(pack_f2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
-          uint32_t pk[16];
+            for (int i = 0; i < 16; ++i)
+              xs[i] = ffma2(pack_f2(__uint_as_float(sv[c][2 * i]), __uint_as_float(sv[c][2 * i + 1])), sc2, nm2);
+            uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0, p1;
-            if (poly_pair(i)) {
-              poly_exp2_x2(xs[i], p0, p1);
-            } else {
-              float x0, x1;
-              unpack_f2(xs[i], x0, x1);
-              p0 = fast_exp2(x0);
-              p1 = fast_exp2(x1);
+            for (int i = 0; i < 16; ++i) {
+              float p0, p1;
+              if (kUsePoly && poly_pair(i, kPoly)) {
+                poly_exp2_fast_x2<kDeg>(xs[i], p0, p1);
+              } else {
+                float x0, x1;
+                unpack_f2(xs[i], x0, x1);
+                p0 = fast_exp2(x0);
+                p1 = fast_exp2(x1);
+              }
+              ls[i & 1] = fadd2(ls[i & 1], pack_f2(p0, p1));
+              pk[i] = pack2<kBF16>(p0, p1);
             }
-            ls[i & 1] = fadd2(ls[i & 1], pack_f2(p0, p1));
-            pk[i] = pack2<kBF16>(p0, p1);
-          }
-          tmem_st16(tP + c * 16, pk);
+            tmem_st16(tP + c * 16, pk);
 #if CSA_PINGPONG
-          if (c == CSA_TOKEN_CHUNK) named_bar_arrive(tok_out, 64);  // the other Q tile may start its exponentials
+            if (c == CSA_TOKEN_CHUNK) named_bar_arrive(tok_out, 64);  // the other Q tile may start its exponentials
 #endif
+          }
+        };
+        if (poly_ok) {
+          exp_pass(std::true_type{});
+        } else {
+          exp_pass(std::false_type{});
         }
         TRACE(7);
         {
@@ -823,6 +864,10 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         }
         named_bar_sync(9, kThreads - 128);  // merge_flag may be rewritten by the next piece only after everyone read it
       }
+#if CSA_TRACE
+      TRACE_CTA(cta_mark, n_mark, e.piece < 0 ? 2 : 3);
+      ++n_mark;
+#endif
     }
 #if CSA_PINGPONG
     // Q tile 1's last hand-over has no taker: absorb it so that no barrier is left half-arrived at exit

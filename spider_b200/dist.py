@@ -200,6 +200,7 @@ class FrameSharding:
         if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' (fused gather + peer-memory scatter) or 'nccl' (all-gather)")
         self.exchange = exchange
+        self.mask_sync = "broadcast"   # or "seeded": see sync_sample()
         self.peers: Optional[PeerExchange] = None
         if not dist.is_initialized():
             raise RuntimeError("FrameSharding needs an initialised torch.distributed process group")
@@ -250,6 +251,17 @@ class FrameSharding:
             buf = sample.view(torch.uint8)
             dist.broadcast(buf, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
                            group=self.group)
+
+    def sync_sample(self, sample: torch.Tensor) -> torch.Tensor:
+        """``post_sample`` hook of ``masks.cal_attn_mask_xl``: returns the device tensor that holds rank 0's draw of
+        a sample vector (in place when it already lives on this rank's device).  ``mask_sync="seeded"``: the ranks
+        seed the generator alike (as ``setup_seed`` does), nothing is sent — the mode a captured step uses."""
+        if self.device is not None and sample.device != torch.device(self.device):
+            sample = sample.to(self.device)
+        if self.mask_sync == "broadcast":
+            dist.broadcast(sample.view(torch.uint8),
+                           src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        return sample
 
     def check_lockstep(self, value: float) -> None:
         """Debug aid: all ranks must have drawn the same gate value (same Python ``random`` seed)."""

@@ -38,6 +38,7 @@ class CompactMask:
         self._dense = dense
         self._lists: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
         self._sample_list = None      # (s_idx, s_count, ranges) — see sample_list()
+        self._rand = None             # resample_(): the uniform draws the sample vector is thresholded from
         self.shared_sample = sample is not None   # rows are (S u own block) by construction; dense: checked
 
     # what the reference's mask tensor exposes and drivers may look at
@@ -96,6 +97,36 @@ class CompactMask:
             self._sample_list = (s_idx.view(-1), s_count, ranges)
         return self._sample_list
 
+    def resample_(self, sa: float, dtype=torch.float16, post_sample=None) -> "CompactMask":
+        """Draw a fresh sample vector INTO the buffers this mask already owns and refresh, in place, whichever index
+        lists were built from the old one — what ``cal_attn_mask_xl`` does at every step roll-over
+        (Comic_Generation.py:119-125) without a single allocation.  Every device pointer a previous step handed to a
+        kernel stays valid and now holds the new step's data, which is what lets a whole denoise step be captured in
+        ONE CUDA graph and replayed (``spider_b200.graph.StepGraph``).  Consumes the device's generator exactly like
+        ``torch.rand((1, T*n), device, dtype) < sa`` (gradio_utils.py:257-258).  ``post_sample`` (multi-GPU: broadcast
+        from rank 0) is applied to the sample vector before the lists are rebuilt."""
+        if self._sample is None:
+            raise ValueError("resample_() needs a mask in sample-vector form")
+        T, F, N = self.total_length, self.id_length, self.n_tokens
+        r = self._rand
+        if r is None or r.dtype != dtype or r.device != self._sample.device:
+            r = self._rand = torch.empty((1, T * N), device=self._sample.device, dtype=dtype)
+        torch.rand((1, T * N), device=r.device, dtype=dtype, out=r)
+        torch.lt(r[0], sa, out=self._sample)
+        if post_sample is not None:
+            got = post_sample(self._sample)
+            if got is not None and got.data_ptr() != self._sample.data_ptr():
+                self._sample.copy_(got)
+        if self._lists is not None:
+            idx, counts = self._lists
+            native.compact_rows(self._sample, T, T * N, 0, block_n=N, limit_cols=F * N, idx=idx, counts=counts)
+        if self._sample_list is not None:
+            s_idx, s_count, ranges = self._sample_list
+            native.compact_rows(self._sample, 1, F * N, 0, idx=s_idx.view(1, -1), counts=s_count)
+            native.sample_ranges(s_idx, s_count, N, F, out=ranges)
+        self._shard_plan = None   # per-rank run lengths read back from the old sample are stale
+        return self
+
     def dense(self) -> torch.Tensor:
         """Materialise the reference's dense mask (debugging / interoperability only; O((T*N)^2) bytes)."""
         if self._dense is not None:
@@ -108,15 +139,39 @@ class CompactMask:
         return rows.unsqueeze(1).repeat(1, N, 1).reshape(-1, T * N)
 
 
-def cal_attn_mask_xl(total_length, id_length, sa32, sa64, height, width, device="cuda", dtype=torch.float16):
+def cal_attn_mask_xl(total_length, id_length, sa32, sa64, height, width, device="cuda", dtype=torch.float16,
+                     reuse=None, post_sample=None):
     """Drop-in for the reference's ``cal_attn_mask_xl`` (same signature, same RNG consumption) that returns two
-    ``CompactMask`` objects instead of two dense tensors."""
+    ``CompactMask`` objects instead of two dense tensors.
+
+    ``reuse=(mask1024, mask4096)``: when both are ``CompactMask`` objects of this geometry that live on ``device``,
+    they are re-sampled IN PLACE (``CompactMask.resample_``) and returned — no allocation, stable device pointers
+    (CUDA-graph replay); anything else is ignored and fresh masks are built."""
     n32 = (height // 32) * (width // 32)   # gradio_utils.py:250
     n16 = (height // 16) * (width // 16)   # gradio_utils.py:251
+    if reuse is not None and _reusable(reuse[0], total_length, id_length, n32, device) and \
+            _reusable(reuse[1], total_length, id_length, n16, device):
+        reuse[0].resample_(sa32, dtype, post_sample)   # :257
+        reuse[1].resample_(sa64, dtype, post_sample)   # :258
+        return reuse[0], reuse[1]
     r32 = torch.rand((1, total_length * n32), device=device, dtype=dtype) < sa32   # :257
     r16 = torch.rand((1, total_length * n16), device=device, dtype=dtype) < sa64   # :258
-    return (CompactMask(total_length, id_length, n32, sample=r32[0]),
-            CompactMask(total_length, id_length, n16, sample=r16[0]))
+    r32, r16 = r32[0], r16[0]
+    if post_sample is not None:
+        r32 = post_sample(r32)
+        r16 = post_sample(r16)
+    return (CompactMask(total_length, id_length, n32, sample=r32),
+            CompactMask(total_length, id_length, n16, sample=r16))
+
+
+def _reusable(cm, total_length, id_length, n_tokens, device) -> bool:
+    if not isinstance(cm, CompactMask) or cm._sample is None:
+        return False
+    dev = torch.device(device)
+    sd = cm._sample.device
+    same_dev = sd.type == dev.type and (dev.index is None or sd.index == dev.index)
+    return (cm.total_length == total_length and cm.id_length == id_length and cm.n_tokens == n_tokens and same_dev
+            and cm._sample.dtype == torch.bool and cm._sample.is_contiguous())
 
 
 def from_dense(mask: torch.Tensor, total_length: int, id_length: int, validate: bool = True) -> CompactMask:

@@ -520,12 +520,18 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, max_rows: int, row_base: i
     return out
 
 
-def sample_ranges(s_idx: torch.Tensor, s_count: torch.Tensor, block_n: int, n_frames: int) -> torch.Tensor:
+def sample_ranges(s_idx: torch.Tensor, s_count: torch.Tensor, block_n: int, n_frames: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ranges [(n_frames+1), 4] int32 (see csa_sample_ranges): the runs of the sampled list each frame attends."""
     flush_batch()   # launches immediately: whatever was deferred before it goes first
     _require_cuda(s_idx, s_count)
     ensure_device(s_idx.device)
-    ranges = torch.empty((n_frames + 1, 4), dtype=torch.int32, device=s_idx.device)
+    if out is not None:
+        if out.dtype != torch.int32 or not out.is_contiguous() or out.numel() != (n_frames + 1) * 4:
+            raise CsaNativeError("sample_ranges: out must be a contiguous int32 tensor of (n_frames + 1) * 4 elements")
+        ranges = out
+    else:
+        ranges = torch.empty((n_frames + 1, 4), dtype=torch.int32, device=s_idx.device)
     rc = load().csa_sample_ranges(s_idx.data_ptr(), s_count.data_ptr(), block_n, n_frames, ranges.data_ptr(),
                                   _stream_ptr(s_idx))
     _check(rc, "csa_sample_ranges")

@@ -75,6 +75,8 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                             # (csa_linear) and the whole call handed over in one batch (csa_run_batch) whenever the
                             # attn module is the plain SDXL attn1 shape (bias-free Linear q/k/v, Linear + Dropout(0)
                             # out, no norms); anything else goes through the module's own projections
+    inplace_masks = True    # step roll-over re-samples the host's CompactMasks IN PLACE when it can (no allocation,
+                            # stable device pointers: a captured denoise step can be replayed, spider_b200/graph.py)
     batched_read = False    # opt-in: a read call may carry R generated frames (batch 2*R, [uncond R,
                             # cond R]); each attends bank + itself exactly like a batch-2 call, in ONE launch.  The
                             # reference generates them one pipe() call at a time (Comic_Generation.py:445-448), so a
@@ -302,11 +304,13 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
         if h.attn_count == h.total_count:
             h.attn_count = 0
             h.cur_step += 1
+            native.flush_batch()
             h.mask1024, h.mask4096 = _masks.cal_attn_mask_xl(
                 self.total_length, self.id_length, h.sa32, h.sa64, h.height, h.width,
-                device=self.device, dtype=self.dtype)
-            if self.dist is not None:
-                self.dist.sync_masks(h.mask1024, h.mask4096)   # every rank must compact the same sample vector
+                device=self.device, dtype=self.dtype,
+                reuse=(h.mask1024, h.mask4096) if self.inplace_masks else None,
+                # every rank must compact the same sample vector: rank 0's draw, before the lists are rebuilt
+                post_sample=self.dist.sync_sample if self.dist is not None else None)
         return out
 
     # ------------------------------------------------------------------------------------------------ branches

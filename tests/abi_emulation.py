@@ -15,8 +15,10 @@ def idx_stride_for(n_cols):
 def compact_rows(mask_rows, n_rows, n_cols, row_stride, block_n=0, limit_cols=0, idx=None, counts=None):
     flat = mask_rows.reshape(-1).to(torch.uint8)
     stride = idx_stride_for(n_cols)
-    idx = torch.zeros((n_rows, stride), dtype=torch.int32)
-    counts = torch.zeros((n_rows,), dtype=torch.int32)
+    if idx is None:      # like the ABI: the caller's buffers are filled in place when it brings them
+        idx = torch.zeros((n_rows, stride), dtype=torch.int32)
+    if counts is None:
+        counts = torch.zeros((n_rows,), dtype=torch.int32)
     for r in range(n_rows):
         row = flat[r * row_stride:r * row_stride + n_cols].bool().clone()
         if block_n > 0:
@@ -28,10 +30,10 @@ def compact_rows(mask_rows, n_rows, n_cols, row_stride, block_n=0, limit_cols=0,
     return idx, counts
 
 
-def sample_ranges(s_idx, s_count, block_n, n_frames):
+def sample_ranges(s_idx, s_count, block_n, n_frames, out=None):
     c = int(s_count.item())
     S = s_idx.reshape(-1)[:c].long()
-    out = torch.zeros((n_frames + 1, 4), dtype=torch.int32)
+    out = torch.zeros((n_frames + 1, 4), dtype=torch.int32) if out is None else out.view(n_frames + 1, 4)
     for f in range(n_frames):
         lo = int(torch.searchsorted(S, torch.tensor(f * block_n)))
         hi = int(torch.searchsorted(S, torch.tensor((f + 1) * block_n)))
