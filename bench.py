@@ -285,12 +285,158 @@ def workload_config(args, n_gpus: int):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+class Workload:
+    """One story write pass on this rank: processors, attention modules, per-layer latents, masks, and a device-side
+    accumulator of sum_f K_f per resolution (what the algorithmic FLOP count needs; read back once after timing)."""
+
+    def __init__(self, args, frames, dev, dtype, world, rank, sharding_cache):
+        import spider_b200
+        from spider_b200.install import make_processor_class
+
+        self.args, self.Fl, self.dev, self.world = args, frames, dev, world
+        Fl, H, W = frames, args.res, args.res
+        self.plan = plan = layer_plan(H, W, args.placement)
+        self.n32 = (H // 32) * (W // 32)
+        self.n16 = (H // 16) * (W // 16)
+        host = self.host = spider_b200.StoryGlobals()
+        host.height, host.width, host.sa32, host.sa64 = H, W, args.sa, args.sa
+        host.id_length, host.total_length = Fl, Fl + 1
+        host.total_count = len(plan)
+        host.write = True
+        cls = make_processor_class(host)
+        cls.native_projections = not args.module_projections
+        self.sharding = None
+        units_local = 2 * Fl
+        if world > 1:
+            from spider_b200.dist import FrameSharding, PeerExchangeUnavailable
+            sharding = sharding_cache.get(Fl)
+            if sharding is None:
+                sharding = sharding_cache[Fl] = FrameSharding(Fl, None, dev, exchange=args.exchange)
+                sharding.mask_sync = "seeded"     # every rank seeds alike; a captured step cannot broadcast
+                if args.exchange == "p2p" and sharding.gc > 1:
+                    try:   # map the peers' buffers now: a box without a peer-memory path falls back as a whole
+                        sharding.prepare_peers({(n, c) for (n, c, h) in plan})
+                    except PeerExchangeUnavailable as e:
+                        if rank == 0:
+                            print(f"bench.py: {e} -> NCCL all-gather", file=sys.stderr, flush=True)
+                        sharding.exchange = args.exchange = "nccl"
+                        sharding.peers = None
+            self.sharding = sharding
+            units_local = sharding.local_batch
+        # identical weights / masks on every rank: same seeds (the mask sample must agree across ranks)
+        torch.manual_seed(0)
+        torch.cuda.manual_seed_all(0)
+        self.attns, self.procs, self.hidden = [], [], []
+        kinds = {}
+        for (n, c, h) in plan:
+            if (n, c, h) not in kinds or not args.share_weights:
+                kinds[(n, c, h)] = SelfAttnModule(c, h).to(dev, dtype)
+            self.attns.append(kinds[(n, c, h)])
+            p = cls(id_length=Fl, device=str(dev), dtype=torch.float16)
+            p.dist = self.sharding
+            self.procs.append(p)
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + rank)
+        for (n, c, h) in plan:
+            self.hidden.append(torch.randn((units_local, n, c), device=dev, dtype=torch.float32, generator=g).to(dtype))
+        # the first step's masks, sampled like the driver does (Comic_Generation.py:376) in compact form; every later
+        # step re-samples them in place (CompactMask.resample_)
+        host.mask1024, host.mask4096 = spider_b200.cal_attn_mask_xl(Fl + 1, Fl, args.sa, args.sa, H, W,
+                                                                    device=str(dev), dtype=torch.float16)
+        self.kf = torch.zeros(2, dtype=torch.int64, device=dev)   # sum over timed steps of sum_f K_f at /32, /16
+        self.steps_counted = 0
+
+    def step(self, count=True):
+        host = self.host
+        host.cur_step = 25       # the bank entry of step 25 is overwritten each time (bounded memory)
+        host.attn_count = 0
+        if count:
+            # K_f = N + the two runs of the sampled list frame f attends (ranges[f] = {start1, len1, start2, len2})
+            Fl = self.Fl
+            r32 = host.mask1024.sample_list(self.dev)[2]
+            r16 = host.mask4096.sample_list(self.dev)[2]
+            self.kf[0] += r32[:Fl, 1].sum() + r32[:Fl, 3].sum() + Fl * self.n32
+            self.kf[1] += r16[:Fl, 1].sum() + r16[:Fl, 3].sum() + Fl * self.n16
+        out = None
+        for a, p, x in zip(self.attns, self.procs, self.hidden):
+            out = p(a, x)
+        return out
+
+    def flops(self) -> float:
+        """algorithmic attention FLOPs of all counted steps, WHOLE job: 4 * d * H * 2 * N * sum_f K_f per layer"""
+        k32, k16 = (int(x) for x in self.kf.tolist())
+        total = 0.0
+        for (n, c, h) in self.plan:
+            total += 4.0 * HEAD_DIM * h * 2 * n * (k32 if n == self.n32 else k16)
+        return total
+
+
+def time_workload(wl, args, steps, warmup, barrier, rank, events=True):
+    """W warm-up steps, then K timed steps bracketed by barriers; returns a dict of measurements of this rank."""
+    from spider_b200 import native
+    from spider_b200.graph import StepGraph
+
+    native.flush_batch()
+    graph = None
+    mode = "eager"
+    with torch.no_grad():
+        for _ in range(max(warmup, 3)):
+            wl.step(count=False)
+        barrier()
+        if events:
+            native.prepare_event_pool(2 * len(wl.plan) * (1 if args.graph else steps) + 8)
+        native.ATTN_EVENTS = None
+        if args.graph:
+            def instrument():
+                # from here on (the capture) the attention launches are bracketed by event-record nodes
+                native.ATTN_EVENTS = [] if events else None
+            try:
+                graph = StepGraph(lambda: wl.step(count=True), wl.dev, warmup=1).capture(before_capture=instrument)
+                mode = "cuda graph (one cudaGraphLaunch per denoise step)"
+            except Exception as e:   # noqa: BLE001 - a driver / torch that cannot capture this step: say so, go eager
+                if rank == 0:
+                    print(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {e}); timing eagerly",
+                          file=sys.stderr, flush=True)
+                graph = None
+                native.abort_batch()
+                torch.cuda.synchronize()
+        if graph is None:
+            native.ATTN_EVENTS = [] if events else None
+        wl.kf.zero_()
+        native.reset_launch_counters()
+        sampler = ClockSampler(wl.dev.index) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_host0 = time.perf_counter()
+        e0.record()
+        if graph is not None:
+            for _ in range(steps):
+                graph.replay()
+        else:
+            for _ in range(steps):
+                wl.step(count=True)
+        e1.record()
+        host_issue_ms = (time.perf_counter() - t_host0) * 1e3   # CPU time to ISSUE the steps (no sync inside)
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        attn_events = native.ATTN_EVENTS or []
+        native.ATTN_EVENTS = None
+        attn_ms = sum(a.elapsed_time(b) for a, b, *_ in attn_events)
+        launches = dict(native.LAUNCHES)
+        if graph is not None:
+            # the launch counters ran at capture; every replay re-executes exactly those launches
+            launches = {k: v * steps for k, v in wl.launches_per_step.items()} if hasattr(wl, "launches_per_step") \
+                else launches
+    return {"ms_total": ms_total, "host_issue_ms": host_issue_ms, "clocks": clocks, "attn_events": len(attn_events),
+            "attn_ms": attn_ms, "attn_steps": (1 if graph is not None else steps), "launches": launches,
+            "mode": mode, "graph": graph}
+
+
 def run_b200_arm(args):
     import torch.distributed as dist
 
-    import spider_b200
     from spider_b200 import native
-    from spider_b200.install import make_processor_class
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -310,163 +456,104 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=dev)
 
     dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}[args.dtype]
-    Fl, H, W = args.frames, args.res, args.res
-    plan = layer_plan(H, W, args.placement)
-
-    host = spider_b200.StoryGlobals()
-    host.height, host.width, host.sa32, host.sa64 = H, W, args.sa, args.sa
-    host.id_length, host.total_length = Fl, Fl + 1
-    host.total_count = len(plan)
-    host.write = True
-    cls = make_processor_class(host)
-    cls.native_projections = not args.module_projections
-
-    sharding = None
-    units_local = 2 * Fl
-    if world > 1:
-        from spider_b200.dist import FrameSharding
-        sharding = FrameSharding(Fl, None, dev, exchange=args.exchange)
-        units_local = sharding.local_batch
-        if args.exchange == "p2p" and sharding.gc > 1:
-            from spider_b200.dist import PeerExchangeUnavailable
-            try:   # map the peers' buffers now: a box without a peer-memory path falls back as a whole, and says so
-                sharding.prepare_peers({(n, c) for (n, c, h) in plan})
-            except PeerExchangeUnavailable as e:
-                if rank == 0:
-                    print(f"bench.py: {e} -> NCCL all-gather", file=sys.stderr, flush=True)
-                sharding.exchange = args.exchange = "nccl"
-                sharding.peers = None
-
-    # identical weights / masks on every rank: same seeds (the mask sample must agree across ranks)
-    torch.manual_seed(0)
-    torch.cuda.manual_seed_all(0)
-    attns, procs, hidden = [], [], []
-    for (n, c, h) in plan:
-        a = SelfAttnModule(c, h).to(dev, dtype)
-        attns.append(a)
-        p = cls(id_length=Fl, device=str(dev), dtype=torch.float16)
-        p.dist = sharding
-        procs.append(p)
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    for (n, c, h) in plan:
-        hidden.append(torch.randn((units_local, n, c), device=dev, dtype=torch.float32, generator=g).to(dtype))
-
-    # the first step's masks, sampled like the driver does (Comic_Generation.py:376) in compact form
-    host.mask1024, host.mask4096 = spider_b200.cal_attn_mask_xl(Fl + 1, Fl, args.sa, args.sa, H, W, device=str(dev),
-                                                                dtype=torch.float16)
-    if sharding is not None:
-        sharding.sync_masks(host.mask1024, host.mask4096)
+    sharding_cache = {}
+    wl = Workload(args, args.frames, dev, dtype, world, rank, sharding_cache)
     real_random = random.random
     random.random = lambda: 0.999   # gate forced open: every call takes the consistent branch (:98-103)
-
-    used_masks = []   # (mask1024, mask4096) used by each timed step, to read K_f back after timing
-
-    def step(record=False):
-        host.cur_step = 25       # the bank entry of step 25 is overwritten each time (bounded memory)
-        host.attn_count = 0
-        if record:
-            used_masks.append((host.mask1024, host.mask4096))
-        out = None
-        for a, p, x in zip(attns, procs, hidden):
-            out = p(a, x)
-        return out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(vals):
+        if world == 1:
+            return vals
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def reduce_sum_int(vals):
+        if world == 1:
+            return vals
+        t = torch.tensor(vals, device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        return [int(x) for x in t]
+
+    extra = {}
     try:
+        # launches of one step, counted on an eager step (a replayed graph re-executes exactly these)
         with torch.no_grad():
-            for _ in range(max(args.warmup, 3)):
-                step()
-            barrier()
-
-            # ------------------------------------------------------------------ value: device-resident inputs
+            for _ in range(2):
+                wl.step(count=False)
+            torch.cuda.synchronize()
             native.reset_launch_counters()
-            native.ATTN_EVENTS = []
-            native.prepare_event_pool(2 * len(plan) * args.steps + 8)   # timing events exist before the timed region
-            sampler = ClockSampler(local_rank) if rank == 0 else None
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            prof = None
-            if args.host_profile and rank == 0:
-                import cProfile
-                prof = cProfile.Profile()
-                prof.enable()
-            t_host0 = time.perf_counter()
-            e0.record()
-            for _ in range(args.steps):
-                step(record=True)
-            e1.record()
-            host_issue_ms = (time.perf_counter() - t_host0) * 1e3   # CPU time to ISSUE the steps (no sync inside)
-            if prof is not None:
-                prof.disable()
-                import io
-                import pstats
-                buf = io.StringIO()
-                pstats.Stats(prof, stream=buf).sort_stats("cumulative").print_stats(45)
-                with open(args.host_profile, "w") as f:
-                    f.write(buf.getvalue())
-            barrier()
-            ms_total = e0.elapsed_time(e1)
-            clocks = sampler.stop() if sampler else None
-            launches = dict(native.LAUNCHES)
-            attn_events = native.ATTN_EVENTS
-            native.ATTN_EVENTS = None
-            attn_ms = sum(a.elapsed_time(b) for a, b, *_ in attn_events)
+            wl.step(count=False)
+            wl.launches_per_step = dict(native.LAUNCHES)
+        m = time_workload(wl, args, args.steps, args.warmup, barrier, rank)
+        flops_total = wl.flops()
 
-            # algorithmic FLOPs of the timed steps from the index lists that were actually used
-            n32 = (H // 32) * (W // 32)
-            flops_total = 0.0
-            for (m32, m16) in used_masks:
-                c32 = m32.lists(dev)[1][:Fl].tolist()
-                c16 = m16.lists(dev)[1][:Fl].tolist()
-                for (n, c, h) in plan:
-                    flops_total += attn_flops(n, h, c32 if n == n32 else c16)
-            # every rank computed its share of the same global work; flops_total is the WHOLE job
+        # ------------------------------------------------------------------ e2e: host buffers in the timed region
+        e2e = None
+        if not args.no_e2e:
+            e2e = run_e2e(args, wl, dev, barrier, rank)
 
-            # ------------------------------------------------------------------ e2e: host buffers in the timed region
-            e2e = None
-            if not args.no_e2e:
-                e2e = run_e2e(args, step_layers=(attns, procs, hidden), host=host, dev=dev, barrier=barrier,
-                              flops_per_step=flops_total / args.steps)
+        # ------------------------------------------------------------------ HBM-bound kernels, timed alone
+        if rank == 0 and not args.no_hbm:
+            extra["roofline_hbm"] = hbm_kernels(args, wl, dev)
+
+        # ------------------------------------------------------------------ config 4: the 16-frame story (N > 1)
+        if args.config4 and world > 1 and args.frames != 16 and 16 % max(1, world // 2) == 0:
+            try:
+                del m["graph"]
+                wl4 = Workload(args, 16, dev, dtype, world, rank, sharding_cache)
+                with torch.no_grad():
+                    wl4.step(count=False)
+                m4 = time_workload(wl4, args, max(2, args.steps // 3), 3, barrier, rank, events=False)
+                ms4 = reduce_max([m4["ms_total"]])[0] / max(2, args.steps // 3)
+                f4 = wl4.flops() / max(2, args.steps // 3)
+                extra["config4"] = {"frames": 16, "ms_per_step": round(ms4, 4),
+                                    "value": round(f4 / (ms4 * 1e-3) / 1e12, 2), "unit": UNIT,
+                                    "tflop_per_step": round(f4 / 1e12, 3), "mode": m4["mode"],
+                                    "n1_ms_per_step_reference": N1_F16_MS,
+                                    "efficiency_vs_n1_ms": round(N1_F16_MS / ms4 / world, 4),
+                                    "note": ("strong scaling of the 16-frame 1024^2 story (BASELINE config 4); "
+                                             "efficiency = (N=1 ms measured by this repo on one B200, "
+                                             "profiles/r02_f16_n1.json) / (N x ms at N GPUs)")}
+                del wl4
+            except Exception as e:   # noqa: BLE001
+                extra["config4"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     finally:
         random.random = real_random
 
-    if world > 1:
-        t = torch.tensor([ms_total, attn_ms, e2e["ms"] if e2e else 0.0], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, attn_ms = float(t[0]), float(t[1])
-        if e2e:
-            e2e["ms"] = float(t[2])
-        lt = torch.tensor([sum(v for k, v in launches.items() if k != "csa_linear"), launches.get("csa_linear", 0)],
-                          device=dev, dtype=torch.int64)
-        dist.all_reduce(lt)
-        total_launches, gemm_launches = int(lt[0]), int(lt[1])
-    else:
-        # our own kernels; the projections are cuBLASLt GEMMs issued through csa_linear and counted separately
-        total_launches = sum(v for k, v in launches.items() if k != "csa_linear")
-        gemm_launches = launches.get("csa_linear", 0)
+    ms_total, attn_ms = reduce_max([m["ms_total"], m["attn_ms"]])
+    if e2e:
+        e2e["ms"] = reduce_max([e2e["ms"]])[0]
+    launches = m["launches"]
+    own = sum(v for k, v in launches.items() if k != "csa_linear")
+    gemm = launches.get("csa_linear", 0)
+    total_launches, gemm_launches = reduce_sum_int([own, gemm])
 
     if rank == 0:
-        ms_step = ms_total / args.steps
-        value = flops_total / args.steps / (ms_step * 1e-3) / 1e12
+        steps = args.steps
+        ms_step = ms_total / steps
+        value = flops_total / steps / (ms_step * 1e-3) / 1e12
         peaks = load_peaks()
-        n_attn = max(1, len(attn_events))
-        achieved = flops_total / world / (attn_ms * 1e-3) / 1e12 if attn_ms > 0 else 0.0
+        n_attn = max(1, m["attn_events"])
+        flops_attn_steps = flops_total / steps * m["attn_steps"]
+        achieved = flops_attn_steps / world / (attn_ms * 1e-3) / 1e12 if attn_ms > 0 else 0.0
         line = {
-            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(args, world),
-            "tflop_per_step": round(flops_total / args.steps / 1e12, 4),
+            "tflop_per_step": round(flops_total / steps / 1e12, 4),
             "gpu_launches": total_launches,
             "library_gemm_launches": gemm_launches,
             "launches_by_entry": launches,
-            "host_issue_ms_per_step": round(host_issue_ms / args.steps, 3),
-            "clocks": clocks,
+            "issue": m["mode"],
+            "host_issue_ms_per_step": round(m["host_issue_ms"] / steps, 3),
+            "clocks": m["clocks"],
             "roofline": {
                 "kernel": "csa_attn_kernel (tcgen05/TMEM flash attention over compacted keys)",
                 "bound": "tensor", "achieved": round(achieved, 2), "peak": peaks["bf16_tflops"], "unit": UNIT,
@@ -474,15 +561,23 @@ def run_b200_arm(args):
                 "peak_source": peaks["source"], "peak_sustained": peaks.get("bf16_tflops_sustained"),
                 "frac_of_sustained": (round(achieved / peaks["bf16_tflops_sustained"], 4)
                                       if peaks.get("bf16_tflops_sustained") else None),
-                "launches_timed": len(attn_events), "avg_launch_ms": round(attn_ms / n_attn, 5),
-                "attn_share_of_step": round(attn_ms / ms_total, 4),
+                "launches_timed": m["attn_events"], "avg_launch_ms": round(attn_ms / n_attn, 5),
+                "timed_over": (f"the attention launches of the last of the {steps} timed steps (event-record nodes "
+                               "inside the replayed graph)" if m["attn_steps"] != steps else
+                               f"all attention launches of the {steps} timed steps"),
+                "attn_share_of_step": round(attn_ms / (ms_total / steps * m["attn_steps"]), 4),
                 "traffic": load_traffic(),
             },
         }
+        line.update(extra)
+        gc = load_comparator()
+        if gc:
+            line["gpu_comparator"] = gc
         if e2e:
-            line["e2e"] = {"value": round(flops_total / args.steps / (e2e["ms"] / args.steps * 1e-3) / 1e12, 2),
-                           "unit": UNIT, "ms_per_step": round(e2e["ms"] / args.steps, 4),
-                           "h2d_bytes_per_step": e2e["h2d"] * world, "d2h_bytes_per_step": e2e["d2h"] * world}
+            line["e2e"] = {"value": round(flops_total / steps / (e2e["ms"] / steps * 1e-3) / 1e12, 2),
+                           "unit": UNIT, "ms_per_step": round(e2e["ms"] / steps, 4),
+                           "h2d_bytes_per_step": e2e["h2d"] * world, "d2h_bytes_per_step": e2e["d2h"] * world,
+                           "issue": e2e["mode"]}
         if world == 1 and not args.no_cpu:
             base = cpu_reference_sample(args, steps=3, warmup=1, whole_step=False)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample")}
@@ -492,29 +587,35 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, step_layers, host, dev, barrier, flops_per_step):
+def run_e2e(args, wl, dev, barrier, rank):
     """The same step through the same processor calls with HOST buffers: per layer the latents are copied from pinned
-    host memory to the device (copy stream, one layer ahead of the compute), the processor runs, and the layer's
-    output is copied back to pinned host memory (second copy stream)."""
-    attns, procs, hidden = step_layers
+    host memory to the device (copy stream, two layers ahead of the compute), the processor runs, and the layer's
+    output is copied back to pinned host memory (second copy stream).  The three streams are captured into ONE graph
+    (fork / join through events) when --graph is on."""
+    from spider_b200 import native
+
+    attns, procs, hidden, host = wl.attns, wl.procs, wl.hidden, wl.host
     host_in = [x.cpu().pin_memory() for x in hidden]
     host_out = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in host_in]
     h2d = sum(x.numel() * x.element_size() for x in host_in)
     d2h = sum(x.numel() * x.element_size() for x in host_out)
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    main = torch.cuda.current_stream(dev)
     depth = 3
     shapes = sorted({tuple(x.shape) for x in hidden})
     ring = {s: [torch.empty(s, device=dev, dtype=hidden[0].dtype) for _ in range(depth)] for s in shapes}
-    ring_free = {s: [None] * depth for s in shapes}   # event: compute finished reading this slot
     n = len(hidden)
+    keep = []
 
     def e2e_step():
+        main = torch.cuda.current_stream(dev)
         host.cur_step = 25
         host.attn_count = 0
+        ring_free = {s: [None] * depth for s in shapes}   # event: compute finished reading this slot
         ready = [None] * n
         slots = [None] * n
         counters = {s: 0 for s in shapes}
+        s_in.wait_stream(main)      # fork (inside a capture this pulls the side streams into it)
+        s_out.wait_stream(main)
 
         def issue_h2d(i):
             s = tuple(hidden[i].shape)
@@ -532,7 +633,6 @@ def run_e2e(args, step_layers, host, dev, barrier, flops_per_step):
         issue_h2d(0)
         if n > 1:
             issue_h2d(1)
-        outs = []
         for i in range(n):
             if i + 2 < n:
                 issue_h2d(i + 2)
@@ -545,20 +645,132 @@ def run_e2e(args, step_layers, host, dev, barrier, flops_per_step):
             with torch.cuda.stream(s_out):
                 s_out.wait_event(done)
                 host_out[i].copy_(out, non_blocking=True)
-            out.record_stream(s_out)
-            outs.append(out)
+            keep.append(out)
+            if len(keep) > 4 * n:
+                del keep[:n]
+        main.wait_stream(s_in)      # join
         main.wait_stream(s_out)
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    return {"ms": e0.elapsed_time(e1), "h2d": h2d, "d2h": d2h}
+    mode = "eager"
+    graph = None
+    with torch.no_grad():
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        if args.graph:
+            try:
+                gs = torch.cuda.Stream(dev)
+                gs.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(gs):
+                    e2e_step()
+                torch.cuda.current_stream(dev).wait_stream(gs)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=gs):
+                    e2e_step()
+                    native.flush_batch()
+                mode = "cuda graph (copies and compute of the three streams in one graph)"
+            except Exception as e:   # noqa: BLE001
+                if rank == 0:
+                    print(f"bench.py: e2e graph capture failed ({type(e).__name__}: {e}); timing eagerly",
+                          file=sys.stderr, flush=True)
+                graph = None
+                torch.cuda.synchronize()
+        for _ in range(1):
+            graph.replay() if graph is not None else e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            graph.replay() if graph is not None else e2e_step()
+        e1.record()
+        barrier()
+    return {"ms": e0.elapsed_time(e1), "h2d": h2d, "d2h": d2h, "mode": mode}
+
+
+def hbm_kernels(args, wl, dev):
+    """The HBM-bound kernels of the path, each timed ALONE with CUDA events on its launching stream (inputs larger than
+    nothing fancy: every call rotates over buffers whose total exceeds the 126 MB L2), algorithmic bytes / time against
+    the measured copy bandwidth (MEASURED_PEAKS.json)."""
+    from spider_b200 import native
+
+    peaks = load_peaks()
+    Fl = wl.Fl
+    out = []
+    dtype = wl.hidden[0].dtype
+
+    def timeit(fn, iters=20):
+        for _ in range(3):
+            fn(0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    for name, n, c in (("32x32", wl.n32, 1280), ("64x64", wl.n16, 640)):
+        cm = wl.host.mask1024 if n == wl.n32 else wl.host.mask4096
+        s_idx, s_count, ranges = cm.sample_list(dev)
+        cnt = int(s_count.item())
+        rot = max(2, int(300e6 // (2 * 2 * Fl * n * c * 2)) + 1)     # rotate sources: > 2 x L2 in flight
+        ks = [torch.randn((2 * Fl * n, c), device=dev, dtype=dtype) for _ in range(rot)]
+        vs = [torch.randn((2 * Fl * n, c), device=dev, dtype=dtype) for _ in range(rot)]
+        ms = timeit(lambda i: native.gather_kv(ks[i % rot], vs[i % rot], Fl * n, 2, s_idx, s_count, Fl * n))
+        nbytes = 2 * 2 * 2 * (cnt + native.CSA_TILE) * c * 2      # groups x {K,V} x (read + write) x rows x C x 2 B
+        out.append({"kernel": f"gather_kv ({name} layer)", "bytes": nbytes, "ms": round(ms, 5),
+                    "achieved": round(nbytes / ms * 1e-6, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(nbytes / ms * 1e-6 / peaks["hbm_gbs"], 4)})
+        del ks, vs
+    # compaction of one step's masks: T rows of T*N bytes read, 4 * sum K_f written — latency-bound by size
+    for name, cm, n in (("32x32", wl.host.mask1024, wl.n32), ("64x64", wl.host.mask4096, wl.n16)):
+        T = Fl + 1
+        idx, counts = cm.lists(dev)
+        ms = timeit(lambda i: native.compact_rows(cm._sample, T, T * n, 0, block_n=n, limit_cols=Fl * n, idx=idx,
+                                                  counts=counts))
+        nbytes = T * T * n + 4 * int(counts.sum().item())
+        out.append({"kernel": f"compact_rows ({name} mask, {T} rows)", "bytes": nbytes, "ms": round(ms, 5),
+                    "achieved": round(nbytes / ms * 1e-6, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(nbytes / ms * 1e-6 / peaks["hbm_gbs"], 4),
+                    "note": "latency-bound: tens of KB per launch"})
+    torch.cuda.empty_cache()
+    return out
+
+
+def _n1_f16_ms() -> float:
+    """16-frame 1024^2 story on ONE B200, ms per denoise step: profiles/r02_f16_n1.json when this round re-measured
+    it (python bench.py --frames 16 --share-weights), else round 1's figure (profiles/r01d_scale)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_f16_n1.json")) as f:
+            return float(json.load(f)["ms_per_step"])
+    except (OSError, ValueError, KeyError):
+        return 158.0
+
+
+N1_F16_MS = _n1_f16_ms()
+
+
+def load_comparator():
+    """Best library kernel on the identical compact problem (tools/bench_torch_sdpa.py run on this pool's B200,
+    committed as profiles/r02_sdpa.json): step-equivalent attention time and TFLOP/s, next to ours from the same run."""
+    path = os.path.join(ROOT, "profiles", "r02_sdpa.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        best = {}
+        for lname, layer in d["layers"].items():
+            cands = [(v["ms"], k) for k, v in layer["compact"].items() if "ms" in v]
+            ms, k = min(cands)
+            best[lname] = {"kernel": k, "ms": ms, "tflops": layer["compact"][k]["tflops"],
+                           "csa_ms": layer["csa"]["ms"], "csa_tflops": layer["csa"]["tflops"]}
+        return {"source": "profiles/r02_sdpa.json (tools/bench_torch_sdpa.py, same B200 pool, compact per-frame "
+                          "problem, keys pre-gathered outside the timed region)",
+                "per_layer": best, "step_equivalent": d.get("step_equivalent"),
+                "reference_dense_masked_call": {k: v for k, v in d["layers"]["64x64"]["dense"].items()}}
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 def load_peaks():
@@ -603,7 +815,13 @@ def main():
     ap.add_argument("--module-projections", action="store_true",
                     help="project through the attn module's nn.Linear layers instead of the library's batched "
                          "csa_linear calls (A/B of the host overhead)")
-    ap.add_argument("--host-profile", default="", help="rank 0: cProfile of the timed loop written to this file")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="issue every step call by call from Python instead of replaying one CUDA graph per step")
+    ap.add_argument("--no-hbm", action="store_true", help="skip the HBM-bound kernels' roofline entries")
+    ap.add_argument("--no-config4", dest="config4", action="store_false",
+                    help="N > 1: do not also time the 16-frame story (BASELINE config 4)")
+    ap.add_argument("--share-weights", action="store_true",
+                    help="one attention module per layer class instead of one per layer (less memory; F = 16)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define CSA_ABI_VERSION 6
+#define CSA_ABI_VERSION 7
 
 #define CSA_E_BADARG (-1)   /* null pointer, non-positive size, misaligned pointer/stride */
 #define CSA_E_SHAPE (-2)    /* unsupported geometry (head_dim != 64, row stride not 16-byte aligned, ...) */
@@ -217,6 +217,8 @@ typedef struct csa_attn_args {
    * needs no host read-back of the sampled counts.  ready_bounds is ignored. */
   int32_t ready_frames_per_peer;
   int32_t _pad2;
+  /* Optional: device uint32 added to ready_epoch on the device (see "Epochs in device memory" below); NULL = 0. */
+  const uint32_t* epoch_base;
 } csa_attn_args_t;
 
 #define CSA_ATTN_NO_SPLIT 1 /* flags: process every unit whole even if a workspace is given */
@@ -253,6 +255,12 @@ int64_t csa_attn_workspace_bytes(int32_t ctas);
  * every r != self: GPU r has finished the attention launch that last read the buffers being overwritten
  * (csa_peer_signal).  `counter` is a zero-initialised local device uint32 (left zero again).
  * Epochs are monotonically increasing uint32 (start at 1, flags zero-initialised).  HBM/NVLink-bound.
+ *
+ * Epochs in device memory.  A denoise step captured in a CUDA graph replays the same kernel arguments, so the epoch a
+ * launch uses cannot be a host value: with `epoch_base` (a device uint32, the same word for every call of a rank)
+ * the kernels use  *epoch_base + epoch  (and  *epoch_base + (int32_t)done_epoch, waiting only if that is > 0), and
+ * csa_epoch_advance — one single-thread kernel at the end of a step, captured with it — adds the number of exchange
+ * calls of the step, so that every replay publishes and awaits fresh, still monotonic epochs.  NULL = host epochs.
  */
 typedef struct csa_peer_scatter_args {
   uint32_t struct_size; /* sizeof(csa_peer_scatter_args_t), checked */
@@ -281,6 +289,7 @@ typedef struct csa_peer_scatter_args {
   const int32_t* ranges;
   int32_t frames_per_peer;
   int32_t idx_adjust;
+  const uint32_t* epoch_base; /* optional, see above */
 } csa_peer_scatter_args_t;
 
 int csa_peer_scatter_kv(const csa_peer_scatter_args_t* args, void* stream);
@@ -288,6 +297,10 @@ int csa_peer_scatter_kv(const csa_peer_scatter_args_t* args, void* stream);
 /* done[r][self] = epoch on every GPU r != self (st.release.sys): everything this GPU enqueued on `stream` before
  * this call — in particular the attention launch that read the exchange buffers of `epoch` — has completed. */
 int csa_peer_signal(uint32_t* const* done, int32_t n_peers, int32_t self, uint32_t epoch, void* stream);
+
+/* *epoch_base += delta on `stream` (single-thread kernel): ends a step whose exchange calls used epochs relative to
+ * *epoch_base (epochs in device memory, above). */
+int csa_epoch_advance(uint32_t* epoch_base, uint32_t delta, void* stream);
 
 /* Enable loads/stores from the current device to memory of `peer_device` (cudaDeviceEnablePeerAccess; already
  * enabled is not an error).  Host-side setup helper. */
@@ -322,7 +335,8 @@ int csa_linear(const csa_linear_args_t* args, void* stream);
  * One processor call = one call into the library: the entries are executed in order on `stream` (projections, K/V
  * gather or peer exchange, attention, output projection), stopping at the first failure (*failed_index = its
  * position, -1 if none; may be NULL).  Purely a host-overhead device: the launches are the ones the single entry
- * points make.  CSA_CALL_EVENT_RECORD records the cudaEvent_t passed as `args` (kernel timing inside a batch).
+ * points make.  CSA_CALL_EVENT_RECORD records the cudaEvent_t passed as `args` (kernel timing inside a batch; on a
+ * capturing stream it becomes an event-record node — cudaEventRecordExternal — whose time can be read after a replay).
  */
 #define CSA_CALL_LINEAR 1
 #define CSA_CALL_ATTN 2
@@ -330,6 +344,7 @@ int csa_linear(const csa_linear_args_t* args, void* stream);
 #define CSA_CALL_PEER_SCATTER 4
 #define CSA_CALL_PEER_SIGNAL 5
 #define CSA_CALL_EVENT_RECORD 6
+#define CSA_CALL_EPOCH_ADVANCE 7
 
 typedef struct csa_gather_kv_args { /* the arguments of csa_gather_kv, in its order */
   const void* k;
@@ -348,13 +363,23 @@ typedef struct csa_gather_kv_args { /* the arguments of csa_gather_kv, in its or
   int32_t row_bytes;
 } csa_gather_kv_args_t;
 
-typedef struct csa_peer_signal_args { /* the arguments of csa_peer_signal */
+typedef struct csa_peer_signal_args { /* the arguments of csa_peer_signal (+ epochs in device memory) */
   uint32_t* done[CSA_MAX_PEERS];
   int32_t n_peers;
   int32_t self;
   uint32_t epoch;
   uint32_t _pad0;
+  const uint32_t* epoch_base; /* optional: the flag value is *epoch_base + epoch */
 } csa_peer_signal_args_t;
+
+/* csa_peer_signal with the argument block (what csa_run_batch executes for CSA_CALL_PEER_SIGNAL). */
+int csa_peer_signal_ex(const csa_peer_signal_args_t* args, void* stream);
+
+typedef struct csa_epoch_advance_args { /* the arguments of csa_epoch_advance, for csa_run_batch */
+  uint32_t* epoch_base;
+  uint32_t delta;
+  uint32_t _pad0;
+} csa_epoch_advance_args_t;
 
 typedef struct csa_call {
   int32_t kind; /* CSA_CALL_* */

@@ -158,6 +158,7 @@ struct AttnKernelParams {
   // into this GPU's memory (csa_peer_scatter_kv); they may be read once ready[r] >= ready_epoch.
   const uint32_t* ready;
   uint32_t ready_epoch;
+  const uint32_t* epoch_base;  // optional: device word added to ready_epoch (steps replayed from a CUDA graph)
   int32_t ready_n;
   int32_t ready_bounds[CSA_MAX_PEERS + 1];
   int32_t ready_fpp;  // > 0: bounds come from `ranges` (frames per peer), not from ready_bounds
@@ -320,6 +321,7 @@ __device__ __forceinline__ void producer_warp(const AttnKernelParams& p, const u
   int ks = 0, vs = 0;
   uint32_t kph = 0, vph = 0, qph = 0;
   uint32_t confirmed = 0;  // peers whose rows of A are known to have landed (multi-GPU)
+  const uint32_t ready_epoch = p.ready_epoch + (p.epoch_base != nullptr ? *p.epoch_base : 0u);
   for (int u = blockIdx.x; u < p.n_sched; u += gridDim.x) {
     const Unit w = decode_unit(p, u);
     if (w.nt == 0) continue;
@@ -390,7 +392,7 @@ __device__ __forceinline__ void producer_warp(const AttnKernelParams& p, const u
               b1 = p.ready_bounds[r + 1];
             }
             if (b0 < hi && b1 > lo) {
-              flag_wait_ge(p.ready + r, p.ready_epoch, 0x130 + r, p.dbg);
+              flag_wait_ge(p.ready + r, ready_epoch, 0x130 + r, p.dbg);
               confirmed |= 1u << r;
             }
           }
@@ -1000,8 +1002,11 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
         if (a->ready_bounds[r] > a->ready_bounds[r + 1])
           return set_error(CSA_E_BADARG, "csa_attn_fwd: ready_bounds must be non-decreasing");
     }
+    if (a->epoch_base != nullptr && (reinterpret_cast<uintptr_t>(a->epoch_base) & 3))
+      return set_error(CSA_E_BADARG, "csa_attn_fwd: epoch_base must be 4-byte aligned");
     p.ready = a->ready;
     p.ready_epoch = a->ready_epoch;
+    p.epoch_base = a->epoch_base;
     p.ready_n = a->ready_n;
     for (int r = 0; r <= a->ready_n; ++r) p.ready_bounds[r] = a->ready_bounds[r];
   }

@@ -158,12 +158,24 @@ extern "C" int csa_run_batch(const csa_call_t* calls, int32_t n_calls, void* str
       case CSA_CALL_PEER_SCATTER: rc = csa_peer_scatter_kv(static_cast<const csa_peer_scatter_args_t*>(a), stream); break;
       case CSA_CALL_PEER_SIGNAL: {
         const csa_peer_signal_args_t* s = static_cast<const csa_peer_signal_args_t*>(a);
-        rc = !s ? set_error(CSA_E_BADARG, "csa_run_batch: null peer_signal args")
-                : csa_peer_signal(s->done, s->n_peers, s->self, s->epoch, stream);
+        rc = !s ? set_error(CSA_E_BADARG, "csa_run_batch: null peer_signal args") : csa_peer_signal_ex(s, stream);
+        break;
+      }
+      case CSA_CALL_EPOCH_ADVANCE: {
+        const csa_epoch_advance_args_t* s = static_cast<const csa_epoch_advance_args_t*>(a);
+        rc = !s ? set_error(CSA_E_BADARG, "csa_run_batch: null epoch_advance args")
+                : csa_epoch_advance(s->epoch_base, s->delta, stream);
         break;
       }
       case CSA_CALL_EVENT_RECORD: {
-        cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(const_cast<void*>(a)), static_cast<cudaStream_t>(stream));
+        // on a capturing stream the record becomes an event-record NODE of the graph (external event): its time can
+        // be read with cudaEventElapsedTime after a replay, which a plainly captured event does not allow
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(static_cast<cudaStream_t>(stream), &cs);
+        cudaError_t e = cudaEventRecordWithFlags(static_cast<cudaEvent_t>(const_cast<void*>(a)),
+                                                 static_cast<cudaStream_t>(stream),
+                                                 cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal
+                                                                                     : cudaEventRecordDefault);
         rc = e == cudaSuccess ? 0 : set_error(static_cast<int>(e), "cudaEventRecord: %s", cudaGetErrorString(e));
         break;
       }

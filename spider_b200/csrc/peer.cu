@@ -27,13 +27,19 @@ struct PeerScatterParams {
   uint32_t* dbg;
   const int32_t* ranges;
   int32_t frames_per_peer, idx_adjust;
+  const uint32_t* epoch_base;
 };
 
 // one warp per (row, K|V): the row is read once (16 B per lane per step) and stored to every peer
 __global__ void __launch_bounds__(256) peer_scatter_kernel(const __grid_constant__ PeerScatterParams p) {
+  // epochs: host values, or offsets to a device-resident base (a step replayed from a CUDA graph)
+  const uint32_t base = p.epoch_base != nullptr ? *p.epoch_base : 0u;
+  const int64_t done_epoch = p.epoch_base != nullptr
+                                 ? static_cast<int64_t>(base) + static_cast<int32_t>(p.done_epoch)
+                                 : static_cast<int64_t>(p.done_epoch);
   // the buffers being overwritten were last read by the peers' attention launches of `done_epoch`
-  if (threadIdx.x < p.n_peers && threadIdx.x != p.self && p.done_epoch > 0)
-    flag_wait_ge(p.done + threadIdx.x, p.done_epoch, 0x400 + threadIdx.x, p.dbg);
+  if (threadIdx.x < p.n_peers && threadIdx.x != p.self && done_epoch > 0)
+    flag_wait_ge(p.done + threadIdx.x, static_cast<uint32_t>(done_epoch), 0x400 + threadIdx.x, p.dbg);
   __syncthreads();
 
   // geometry: from the host, or from the device-resident runs of the sampled list
@@ -76,7 +82,7 @@ __global__ void __launch_bounds__(256) peer_scatter_kernel(const __grid_constant
     if (prev == gridDim.x - 1) {
       *p.counter = 0u;
       __threadfence_system();   // orders every block's stores (observed through the counter) before the flags
-      for (int r = 0; r < p.n_peers; ++r) st_relaxed_sys(p.ready[r] + p.self, p.epoch);
+      for (int r = 0; r < p.n_peers; ++r) st_relaxed_sys(p.ready[r] + p.self, base + p.epoch);
     }
   }
 }
@@ -85,15 +91,19 @@ struct PeerSignalParams {
   uint32_t* done[CSA_MAX_PEERS];
   int32_t n_peers, self;
   uint32_t epoch;
+  const uint32_t* epoch_base;
 };
 
 __global__ void peer_signal_kernel(const __grid_constant__ PeerSignalParams p) {
   const int r = threadIdx.x;
   if (r < p.n_peers && r != p.self) {
+    const uint32_t base = p.epoch_base != nullptr ? *p.epoch_base : 0u;
     __threadfence_system();
-    st_release_sys(p.done[r] + p.self, p.epoch);
+    st_release_sys(p.done[r] + p.self, base + p.epoch);
   }
 }
+
+__global__ void epoch_advance_kernel(uint32_t* base, uint32_t delta) { *base += delta; }
 
 }  // namespace csa
 
@@ -114,6 +124,8 @@ extern "C" int csa_peer_scatter_kv(const csa_peer_scatter_args_t* a, void* strea
   if (!a->k || !a->v || !a->done || !a->counter || (a->count > 0 && !a->idx) || !al16(a->k) || !al16(a->v))
     return set_error(CSA_E_BADARG, "csa_peer_scatter_kv: null or misaligned pointer");
   if (a->epoch == 0) return set_error(CSA_E_BADARG, "csa_peer_scatter_kv: epochs start at 1");
+  if (a->epoch_base != nullptr && (reinterpret_cast<uintptr_t>(a->epoch_base) & 3))
+    return set_error(CSA_E_BADARG, "csa_peer_scatter_kv: epoch_base must be 4-byte aligned");
   PeerScatterParams p;
   memset(&p, 0, sizeof(p));
   for (int r = 0; r < a->n_peers; ++r) {
@@ -137,6 +149,7 @@ extern "C" int csa_peer_scatter_kv(const csa_peer_scatter_args_t* a, void* strea
   p.done_epoch = a->done_epoch;
   p.done = a->done;
   p.counter = a->counter;
+  p.epoch_base = a->epoch_base;
   p.dbg = debug_record_devptr();
   if (a->ranges != nullptr) {
     if (a->frames_per_peer <= 0 || (reinterpret_cast<uintptr_t>(a->ranges) & 15) || !a->idx)
@@ -156,7 +169,8 @@ extern "C" int csa_peer_scatter_kv(const csa_peer_scatter_args_t* a, void* strea
   return 0;
 }
 
-extern "C" int csa_peer_signal(uint32_t* const* done, int32_t n_peers, int32_t self, uint32_t epoch, void* stream) {
+static int peer_signal_launch(uint32_t* const* done, int32_t n_peers, int32_t self, uint32_t epoch,
+                              const uint32_t* epoch_base, void* stream) {
   if (!done || n_peers < 1 || n_peers > CSA_MAX_PEERS || self < 0 || self >= n_peers)
     return set_error(CSA_E_BADARG, "csa_peer_signal: bad arguments");
   PeerSignalParams p;
@@ -168,9 +182,28 @@ extern "C" int csa_peer_signal(uint32_t* const* done, int32_t n_peers, int32_t s
   p.n_peers = n_peers;
   p.self = self;
   p.epoch = epoch;
+  p.epoch_base = epoch_base;
   peer_signal_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(static_cast<int>(e), "peer_signal_kernel: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int csa_peer_signal(uint32_t* const* done, int32_t n_peers, int32_t self, uint32_t epoch, void* stream) {
+  return peer_signal_launch(done, n_peers, self, epoch, nullptr, stream);
+}
+
+extern "C" int csa_peer_signal_ex(const csa_peer_signal_args_t* a, void* stream) {
+  if (!a) return set_error(CSA_E_BADARG, "csa_peer_signal_ex: null args");
+  return peer_signal_launch(a->done, a->n_peers, a->self, a->epoch, a->epoch_base, stream);
+}
+
+extern "C" int csa_epoch_advance(uint32_t* epoch_base, uint32_t delta, void* stream) {
+  if (!epoch_base || (reinterpret_cast<uintptr_t>(epoch_base) & 3))
+    return set_error(CSA_E_BADARG, "csa_epoch_advance: null or misaligned epoch_base");
+  epoch_advance_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(epoch_base, delta);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(static_cast<int>(e), "epoch_advance_kernel: %s", cudaGetErrorString(e));
   return 0;
 }
 

@@ -24,8 +24,10 @@ re-drawn (``sync_masks``), and the per-rank run lengths are read back once per s
 per mask, shared by all layers).  The branch gate uses Python's ``random`` and must be seeded identically on every
 rank (as ``setup_seed`` does, Comic_Generation.py:35-40); ``check_lockstep`` asserts it.
 
-Read passes (one generated frame per call, batch 2) are independent given the bank and are not sharded here: run
-them on the rank(s) that hold the bank.  A sharded write pass keeps a sharded bank.
+Read passes (one generated frame per call, batch 2; Comic_Generation.py:441-448) are independent given the bank: a
+sharded write pass leaves every rank with the K/V of its own frames, the first read of a (layer, step) entry
+all-gathers it into the full bank on every rank (``gather_bank``, one NCCL collective per entry), and from then on
+any rank can generate any frame — run different frames on different ranks, no per-layer exchange.
 """
 from __future__ import annotations
 
@@ -70,7 +72,12 @@ class PeerExchange:
     (``ready``) and release (``done``) flags, each mapped into every peer (CUDA IPC + P2P access).  Layer calls are
     numbered by a monotonically increasing epoch (all ranks make the same calls in the same order); epoch e uses
     slot e % 2, so a rank may run one layer ahead of the slowest peer before ``csa_peer_scatter_kv`` has to wait
-    for that peer's ``done`` flag."""
+    for that peer's ``done`` flag.
+
+    Epochs live in device memory: a call passes its number WITHIN the current step, the kernels add the
+    device-resident ``epoch_base``, and ``end_step()`` — called by the processor at the step roll-over — advances the
+    base by the (even) number of calls of the step with one single-thread kernel.  A denoise step captured in a CUDA
+    graph therefore publishes and awaits fresh epochs at every replay (``spider_b200/graph.py``)."""
 
     SLOTS = 2
 
@@ -78,7 +85,8 @@ class PeerExchange:
         self.sh = sh
         self.device = torch.device(device)
         self.cap_bytes = 0
-        self.epoch = 0
+        self.epoch = 0        # exchange calls since the last end_step() (the device holds the base)
+        self.epoch_base = None
         self.bufs = None      # per rank: uint8 tensor [SLOTS * 2 * cap_bytes]
         self.flags = None     # per rank: int32 tensor [3, CSA_MAX_PEERS]: ready, done, {counter, ...}
         self._keep = None
@@ -96,6 +104,10 @@ class PeerExchange:
         cap = (need_bytes + 4095) // 4096 * 4096
         local = torch.zeros(self.SLOTS * 2 * cap, dtype=torch.uint8, device=self.device)
         flags = torch.zeros(3 * native.CSA_MAX_PEERS * 4, dtype=torch.uint8, device=self.device)
+        if self.epoch_base is None:
+            self.epoch_base = torch.zeros(1, dtype=torch.int32, device=self.device)
+        else:
+            self.epoch_base.zero_()                 # fresh flags: epochs restart
         if self.device.type == "cuda":
             torch.cuda.synchronize(self.device)    # the zeros are in memory before anybody maps the buffers
         handles = [None] * sh.gc
@@ -131,6 +143,20 @@ class PeerExchange:
         self.epoch = 0    # fresh flags: epochs restart
         self.allocations += 1
         dist.barrier(group=sh.half_group)          # every rank has mapped every buffer before the first store
+
+    def end_step(self) -> None:
+        """The step's exchange calls are over: fold their count into the device-resident base (kept even so that the
+        slot of a call, epoch % SLOTS, is the same in every step)."""
+        if self.epoch == 0 or self.epoch_base is None:
+            return
+        if self.epoch % self.SLOTS:
+            # an odd step: pad it with an epoch that moves no data but IS released (a later scatter into that slot
+            # waits for done >= its epoch - SLOTS, which may be this one)
+            self.epoch += 1
+            native.peer_signal(self._done, self.sh.rank_in_half, self.epoch, self.epoch_base,
+                               epoch_base=self.epoch_base)
+        native.epoch_advance(self.epoch_base, self.epoch)
+        self.epoch = 0
 
     def views(self, slot: int, rows: int, cols: int, dtype):
         """Per rank the (K[S], V[S]) views [rows, cols] of ``slot`` (cached: the same few layer shapes recur)."""
@@ -342,14 +368,39 @@ class FrameSharding:
         # Geometry stays on the device (no read-back of the sampled counts): the scatter kernel finds this rank's run
         # of S in `ranges`, the attention kernel the peers' bounds.  Peers last read this slot in epoch - SLOTS.
         native.peer_scatter_kv(k, v, pl.s_idx, fr * N, 0, ks, vs, ex.ready(), me, epoch,
-                               ex.done()[me], max(0, epoch - ex.SLOTS), ex.counter(),
-                               ranges=pl.ranges, frames_per_peer=fr, idx_adjust=-self.f0 * N)
-        sent = self._p2p_sent.setdefault(id(pl), [pl, 0])
+                               ex.done()[me], epoch - ex.SLOTS, ex.counter(),
+                               ranges=pl.ranges, frames_per_peer=fr, idx_adjust=-self.f0 * N,
+                               epoch_base=ex.epoch_base)
+        sent = self._p2p_sent.setdefault(id(pl.cm), [pl, 0])   # per mask object (masks are re-sampled in place)
+        sent[0] = pl
         sent[1] += (self.gc - 1) * 2 * C * k.element_size()
         native.attn_fwd(q, o, heads=heads, n_groups=1, n_frames=fr, n_q=N,
                         k_a=ks[me], v_a=vs[me], a_group_rows=rows, ranges=pl.ranges, range_base=self.f0,
                         range_step=1, k_b=k, v_b=v, b_group_rows=fr * N, cb=(0, N, N),
                         b_first=True, ready=ex.ready()[me], ready_epoch=epoch, ready_peers=self.gc,
-                        ready_frames_per_peer=fr)
-        native.peer_signal(ex.done(), me, epoch, q)
+                        ready_frames_per_peer=fr, epoch_base=ex.epoch_base)
+        native.peer_signal(ex.done(), me, epoch, q, epoch_base=ex.epoch_base)
         return o
+
+    def end_step(self) -> None:
+        """Called by the processor at the step roll-over (every rank makes the same calls)."""
+        if self.peers is not None:
+            self.peers.end_step()
+
+    # ---------------------------------------------------------------------------------------------- the bank
+    def gather_bank(self, k: torch.Tensor, v: torch.Tensor):
+        """All-gather the K/V rows a sharded write pass left on this rank (its own frames of its CFG half) into the
+        full id_bank layout ``[uncond frames 0..F-1, cond frames 0..F-1]`` — rank order is exactly that order — so
+        that read passes (Comic_Generation.py:441-448: one generated frame per call, independent given the bank) can
+        run on any rank, different frames on different ranks.  One collective per (layer, step), done lazily by the
+        first read of that entry; the result replaces the shard in the bank."""
+        native.flush_batch()
+        rows, C = k.shape
+        ks = k.contiguous()
+        vs = v.contiguous()
+        kf = torch.empty((self.world * rows, C), dtype=k.dtype, device=k.device)
+        vf = torch.empty_like(kf)
+        dist.all_gather_into_tensor(kf.view(-1), ks.view(-1), group=self.group)
+        dist.all_gather_into_tensor(vf.view(-1), vs.view(-1), group=self.group)
+        self._bytes_exchanged += 2 * (self.world - 1) * ks.numel() * ks.element_size()
+        return kf, vf

@@ -8,6 +8,7 @@ PyTorch is used here only for device memory (``tensor.data_ptr()``) and for the 
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint8, c_uint32, c_void_p
@@ -19,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CSA_B200_LIB: developer knob to load an experimental build of the same ABI (kernel tuning sweeps); default in-tree
 LIB_PATH = os.environ.get("CSA_B200_LIB") or os.path.join(_HERE, "libcsa_b200.so")
 
-CSA_ABI_VERSION = 6
+CSA_ABI_VERSION = 7
 CSA_DTYPE_F16 = 0
 CSA_DTYPE_BF16 = 1
 CSA_TILE = 128
@@ -43,6 +44,8 @@ EXPORTED_SYMBOLS = (
     "csa_debug_last_launch",
     "csa_peer_scatter_kv",
     "csa_peer_signal",
+    "csa_peer_signal_ex",
+    "csa_epoch_advance",
     "csa_enable_peer_access",
     "csa_ipc_export",
     "csa_ipc_open",
@@ -109,6 +112,7 @@ class CsaAttnArgs(ctypes.Structure):
         ("ready_bounds", c_int32 * (CSA_MAX_PEERS + 1)),
         ("ready_frames_per_peer", c_int32),
         ("_pad2", c_int32),
+        ("epoch_base", c_void_p),
     ]
 
 
@@ -137,6 +141,7 @@ class CsaPeerScatterArgs(ctypes.Structure):
         ("ranges", c_void_p),
         ("frames_per_peer", c_int32),
         ("idx_adjust", c_int32),
+        ("epoch_base", c_void_p),
     ]
 
 
@@ -191,7 +196,14 @@ class CsaPeerSignalArgs(ctypes.Structure):
         ("self_", c_int32),
         ("epoch", c_uint32),
         ("_pad0", c_uint32),
+        ("epoch_base", c_void_p),
     ]
+
+
+class CsaEpochAdvanceArgs(ctypes.Structure):
+    """Mirror of ``csa_epoch_advance_args_t``."""
+
+    _fields_ = [("epoch_base", c_void_p), ("delta", c_uint32), ("_pad0", c_uint32)]
 
 
 class CsaCall(ctypes.Structure):
@@ -201,7 +213,7 @@ class CsaCall(ctypes.Structure):
 
 
 CSA_CALL_LINEAR, CSA_CALL_ATTN, CSA_CALL_GATHER_KV, CSA_CALL_PEER_SCATTER, CSA_CALL_PEER_SIGNAL, \
-    CSA_CALL_EVENT_RECORD = 1, 2, 3, 4, 5, 6
+    CSA_CALL_EVENT_RECORD, CSA_CALL_EPOCH_ADVANCE = 1, 2, 3, 4, 5, 6, 7
 
 CSA_ATTN_NO_SPLIT = 1
 CSA_ATTN_B_FIRST = 2
@@ -213,7 +225,7 @@ _lib: Optional[ctypes.CDLL] = None
 # attention launches on the launching stream; both are read by bench.py.
 LAUNCHES = {"csa_attn_fwd": 0, "csa_compact_rows": 0, "csa_validate_mask": 0, "csa_gather_rows": 0,
             "csa_sample_ranges": 0, "csa_gather_kv": 0, "csa_peer_scatter_kv": 0, "csa_peer_signal": 0,
-            "csa_linear": 0}
+            "csa_linear": 0, "csa_epoch_advance": 0}
 ATTN_EVENTS: Optional[list] = None   # when a list: (start_event, end_event, n_groups, n_frames, n_q, heads) appended
 
 
@@ -270,6 +282,10 @@ def load() -> ctypes.CDLL:
     lib.csa_peer_scatter_kv.argtypes = [POINTER(CsaPeerScatterArgs), c_void_p]
     lib.csa_peer_signal.restype = c_int32
     lib.csa_peer_signal.argtypes = [POINTER(c_void_p), c_int32, c_int32, c_uint32, c_void_p]
+    lib.csa_peer_signal_ex.restype = c_int32
+    lib.csa_peer_signal_ex.argtypes = [POINTER(CsaPeerSignalArgs), c_void_p]
+    lib.csa_epoch_advance.restype = c_int32
+    lib.csa_epoch_advance.argtypes = [c_void_p, c_uint32, c_void_p]
     lib.csa_enable_peer_access.restype = c_int32
     lib.csa_enable_peer_access.argtypes = [c_int32]
     lib.csa_ipc_export.restype = c_int32
@@ -317,6 +333,18 @@ def _require_cuda(*tensors: torch.Tensor) -> None:
 
 
 _checked_devices: set = set()
+_NULL_CTX = contextlib.nullcontext()
+
+
+def _on_device_of(t: torch.Tensor):
+    """Context that makes ``t``'s device the current CUDA device for a native call.  The library launches on the
+    CURRENT device (``<<<>>>``, cuBLASLt, cudaGetDevice for the SM count) but takes its stream from the tensor's
+    device: with a pipeline on cuda:1 while cuda:0 is current the two would disagree — an illegal address without
+    peer access, silently the wrong GPU with it.  PyTorch ops guard this themselves; so do we."""
+    idx = t.device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NULL_CTX
+    return torch.cuda.device(idx)
 
 
 def ensure_device(device: torch.device) -> None:
@@ -347,17 +375,19 @@ def dtype_code(dt: torch.dtype) -> int:
 # code that has to do so calls flush_batch() first.
 _BATCH: Optional[list] = None
 _BATCH_STREAM: int = 0
+_BATCH_LIKE: Optional[torch.Tensor] = None   # a tensor of the batch's device (device guard at flush)
 _BATCH_NAMES = {CSA_CALL_LINEAR: "csa_linear", CSA_CALL_ATTN: "csa_attn_fwd", CSA_CALL_GATHER_KV: "csa_gather_kv",
                 CSA_CALL_PEER_SCATTER: "csa_peer_scatter_kv", CSA_CALL_PEER_SIGNAL: "csa_peer_signal",
-                CSA_CALL_EVENT_RECORD: "cudaEventRecord"}
+                CSA_CALL_EVENT_RECORD: "cudaEventRecord", CSA_CALL_EPOCH_ADVANCE: "csa_epoch_advance"}
 
 
 def begin_batch(like: torch.Tensor) -> None:
-    global _BATCH, _BATCH_STREAM
+    global _BATCH, _BATCH_STREAM, _BATCH_LIKE
     if _BATCH is not None:
         flush_batch()
     _BATCH = []
     _BATCH_STREAM = _stream_ptr(like)
+    _BATCH_LIKE = like
 
 
 def flush_batch() -> None:
@@ -372,7 +402,8 @@ def flush_batch() -> None:
         arr[i].kind = kind
         arr[i].args = a if isinstance(a, int) else ctypes.addressof(a)
     failed = c_int32(-1)
-    rc = load().csa_run_batch(arr, n, _BATCH_STREAM, ctypes.byref(failed))
+    with (_on_device_of(_BATCH_LIKE) if _BATCH_LIKE is not None else _NULL_CTX):
+        rc = load().csa_run_batch(arr, n, _BATCH_STREAM, ctypes.byref(failed))
     if rc != 0:
         what = _BATCH_NAMES.get(calls[failed.value][0], "?") if 0 <= failed.value < n else "csa_run_batch"
         _check(rc, f"{what} (entry {failed.value} of a batch of {n})")
@@ -384,12 +415,13 @@ def abort_batch() -> None:
     _BATCH = None
 
 
-def _issue(kind: int, a, direct, what: str, stream: int) -> None:
-    """Launch now, or defer into the open batch (same stream only)."""
+def _issue(kind: int, a, direct, what: str, stream: int, like: Optional[torch.Tensor] = None) -> None:
+    """Launch now (with ``like``'s device current), or defer into the open batch (same stream only)."""
     if _BATCH is not None and stream == _BATCH_STREAM:
         _BATCH.append((kind, a))
     else:
-        _check(direct(stream), what)
+        with (_on_device_of(like) if like is not None else _NULL_CTX):
+            _check(direct(stream), what)
 
 
 _EVENT_POOL: list = []
@@ -402,6 +434,20 @@ def _pooled_event() -> "torch.cuda.Event":
     e = torch.cuda.Event(enable_timing=True)
     e.record()
     return e
+
+
+def record_event(ev: "torch.cuda.Event", stream: int) -> None:
+    """Record a timing event through the library (CSA_CALL_EVENT_RECORD): on a stream that is being captured into a
+    CUDA graph this makes an event-record NODE whose time can be read after a replay, which torch's own
+    ``Event.record()`` (a plainly captured event) does not allow."""
+    if _BATCH is not None and stream == _BATCH_STREAM:
+        _BATCH.append((CSA_CALL_EVENT_RECORD, ev.cuda_event))
+        return
+    arr = (CsaCall * 1)()
+    arr[0].kind = CSA_CALL_EVENT_RECORD
+    arr[0].args = ev.cuda_event
+    failed = c_int32(-1)
+    _check(load().csa_run_batch(arr, 1, stream, ctypes.byref(failed)), "cudaEventRecord")
 
 
 def prepare_event_pool(n: int) -> None:
@@ -451,7 +497,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     ws = _linear_workspace(x.device)
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     lib = load()
-    _issue(CSA_CALL_LINEAR, a, lambda st: lib.csa_linear(ctypes.byref(a), st), "csa_linear", _stream_ptr(x))
+    _issue(CSA_CALL_LINEAR, a, lambda st: lib.csa_linear(ctypes.byref(a), st), "csa_linear", _stream_ptr(x), x)
     LAUNCHES["csa_linear"] += 1
     return out
 
@@ -478,8 +524,9 @@ def compact_rows(mask_rows: torch.Tensor, n_rows: int, n_cols: int, row_stride: 
         idx = torch.empty((n_rows, stride), dtype=torch.int32, device=mask_rows.device)
     if counts is None:
         counts = torch.empty((n_rows,), dtype=torch.int32, device=mask_rows.device)
-    rc = load().csa_compact_rows(mask_rows.data_ptr(), row_stride, n_rows, n_cols, block_n, limit_cols,
-                                 idx.data_ptr(), idx.stride(0), counts.data_ptr(), _stream_ptr(mask_rows))
+    with _on_device_of(mask_rows):
+        rc = load().csa_compact_rows(mask_rows.data_ptr(), row_stride, n_rows, n_cols, block_n, limit_cols,
+                                     idx.data_ptr(), idx.stride(0), counts.data_ptr(), _stream_ptr(mask_rows))
     _check(rc, "csa_compact_rows")
     LAUNCHES["csa_compact_rows"] += 1
     return idx, counts
@@ -493,8 +540,9 @@ def validate_mask(mask: torch.Tensor, block_n: int) -> torch.Tensor:
     if mask.dim() != 2 or mask.stride(1) != 1:
         raise CsaNativeError("validate_mask expects a 2-D mask with unit column stride")
     n_bad = torch.zeros((1,), dtype=torch.int32, device=mask.device)
-    rc = load().csa_validate_mask(mask.data_ptr(), mask.stride(0), mask.shape[0], mask.shape[1], block_n,
-                                  n_bad.data_ptr(), _stream_ptr(mask))
+    with _on_device_of(mask):
+        rc = load().csa_validate_mask(mask.data_ptr(), mask.stride(0), mask.shape[0], mask.shape[1], block_n,
+                                      n_bad.data_ptr(), _stream_ptr(mask))
     _check(rc, "csa_validate_mask")
     LAUNCHES["csa_validate_mask"] += 1
     return n_bad
@@ -512,9 +560,10 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, max_rows: int, row_base: i
     es = src.element_size()
     if out is None:
         out = torch.empty((max_rows, src.shape[1]), dtype=src.dtype, device=src.device)
-    rc = load().csa_gather_rows(src.data_ptr(), src.stride(0) * es, row_base, idx.data_ptr(),
-                                count.data_ptr() if count is not None else None, count_adjust, max_rows,
-                                out.data_ptr(), out.stride(0) * es, src.shape[1] * es, _stream_ptr(src))
+    with _on_device_of(src):
+        rc = load().csa_gather_rows(src.data_ptr(), src.stride(0) * es, row_base, idx.data_ptr(),
+                                    count.data_ptr() if count is not None else None, count_adjust, max_rows,
+                                    out.data_ptr(), out.stride(0) * es, src.shape[1] * es, _stream_ptr(src))
     _check(rc, "csa_gather_rows")
     LAUNCHES["csa_gather_rows"] += 1
     return out
@@ -532,8 +581,9 @@ def sample_ranges(s_idx: torch.Tensor, s_count: torch.Tensor, block_n: int, n_fr
         ranges = out
     else:
         ranges = torch.empty((n_frames + 1, 4), dtype=torch.int32, device=s_idx.device)
-    rc = load().csa_sample_ranges(s_idx.data_ptr(), s_count.data_ptr(), block_n, n_frames, ranges.data_ptr(),
-                                  _stream_ptr(s_idx))
+    with _on_device_of(s_idx):
+        rc = load().csa_sample_ranges(s_idx.data_ptr(), s_count.data_ptr(), block_n, n_frames, ranges.data_ptr(),
+                                      _stream_ptr(s_idx))
     _check(rc, "csa_sample_ranges")
     LAUNCHES["csa_sample_ranges"] += 1
     return ranges
@@ -561,7 +611,7 @@ def gather_kv(k: torch.Tensor, v: torch.Tensor, group_rows: int, n_groups: int, 
     _issue(CSA_CALL_GATHER_KV, a,
            lambda st: lib.csa_gather_kv(a.k, a.v, a.ld_bytes, a.group_rows, a.n_groups, a.s_idx, a.s_count, a.max_rows,
                                         a.k_out, a.v_out, a.out_ld_bytes, a.out_group_rows, a.row_bytes, st),
-           "csa_gather_kv", _stream_ptr(k))
+           "csa_gather_kv", _stream_ptr(k), k)
     LAUNCHES["csa_gather_kv"] += 1
     return k_s, v_s, out_group_rows
 
@@ -596,7 +646,7 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
              max_ctas: int = 0, ranges: Optional[torch.Tensor] = None, range_base: int = 0,
              range_step: int = 0, split=True, b_first: bool = False, ready: Optional[torch.Tensor] = None,
              ready_epoch: int = 0, ready_bounds=None, ready_peers: int = 0,
-             ready_frames_per_peer: int = 0) -> torch.Tensor:
+             ready_frames_per_peer: int = 0, epoch_base: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Launch csa_attn_fwd on the current stream.  All matrices are 2-D ``(rows, heads*64)`` with unit column stride."""
     _require_cuda(q, o)
     ensure_device(q.device)
@@ -644,6 +694,8 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
         if ready.dtype != torch.int32 or not ready.is_contiguous() or ready.numel() < n or not 1 <= n <= CSA_MAX_PEERS:
             raise CsaNativeError("ready must be a contiguous int32 tensor with one flag per peer (<= 8 peers)")
         a.ready, a.ready_epoch, a.ready_n = ready.data_ptr(), ready_epoch, n
+        if epoch_base is not None:
+            a.epoch_base = epoch_base.data_ptr()
         if ready_frames_per_peer > 0:
             a.ready_frames_per_peer = ready_frames_per_peer
         else:
@@ -662,17 +714,12 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
     if ATTN_EVENTS is not None:
         # kernel time of the attention launches on the launching stream (bench.py's roofline line)
         e0, e1 = _pooled_event(), _pooled_event()
-        if _BATCH is not None and stream == _BATCH_STREAM:
-            _BATCH.append((CSA_CALL_EVENT_RECORD, e0.cuda_event))
-            _BATCH.append((CSA_CALL_ATTN, a))
-            _BATCH.append((CSA_CALL_EVENT_RECORD, e1.cuda_event))
-        else:
-            e0.record()
-            _check(direct(stream), "csa_attn_fwd")
-            e1.record()
+        record_event(e0, stream)
+        _issue(CSA_CALL_ATTN, a, direct, "csa_attn_fwd", stream, q)
+        record_event(e1, stream)
         ATTN_EVENTS.append((e0, e1, n_groups, n_frames, n_q, heads))
     else:
-        _issue(CSA_CALL_ATTN, a, direct, "csa_attn_fwd", stream)
+        _issue(CSA_CALL_ATTN, a, direct, "csa_attn_fwd", stream, q)
     LAUNCHES["csa_attn_fwd"] += 1
     return o
 
@@ -680,7 +727,7 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
 def peer_scatter_kv(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, count: int, dst_row0: int, k_dst, v_dst,
                     ready, self_index: int, epoch: int, done: torch.Tensor, done_epoch: int,
                     counter: torch.Tensor, ranges: Optional[torch.Tensor] = None, frames_per_peer: int = 0,
-                    idx_adjust: int = 0) -> None:
+                    idx_adjust: int = 0, epoch_base: Optional[torch.Tensor] = None) -> None:
     """Store this GPU's sampled K/V rows into the S-ordered buffers of every GPU of the group and raise its arrival
     flag there (see csa_peer_scatter_kv).  ``k_dst / v_dst / ready`` are lists of tensors, one per GPU (peer memory;
     entry ``self_index`` is local); ``done`` and ``counter`` are local.  With ``ranges`` the geometry is read on the
@@ -710,17 +757,21 @@ def peer_scatter_kv(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, count: 
         ld = kd.stride(0)
         a.k_dst[r], a.v_dst[r], a.ready[r] = kd.data_ptr(), vd.data_ptr(), ready[r].data_ptr()
     a.dst_ld_bytes = ld * es
-    a.epoch, a.done_epoch = epoch, done_epoch
+    # with epoch_base both are offsets to the device-resident base; done_epoch may then be <= 0 (two's complement)
+    a.epoch, a.done_epoch = epoch, done_epoch & 0xffffffff
     a.done, a.counter = done.data_ptr(), counter.data_ptr()
+    if epoch_base is not None:
+        a.epoch_base = epoch_base.data_ptr()
     if ranges is not None:
         a.ranges, a.frames_per_peer, a.idx_adjust = ranges.data_ptr(), frames_per_peer, idx_adjust
     lib = load()
     _issue(CSA_CALL_PEER_SCATTER, a, lambda st: lib.csa_peer_scatter_kv(ctypes.byref(a), st), "csa_peer_scatter_kv",
-           _stream_ptr(k))
+           _stream_ptr(k), k)
     LAUNCHES["csa_peer_scatter_kv"] += 1
 
 
-def peer_signal(done, self_index: int, epoch: int, like: torch.Tensor) -> None:
+def peer_signal(done, self_index: int, epoch: int, like: torch.Tensor,
+                epoch_base: Optional[torch.Tensor] = None) -> None:
     """done[r][self_index] = epoch on every other GPU r, ordered after everything enqueued so far on the current
     stream of ``like``'s device (see csa_peer_signal)."""
     n = len(done)
@@ -728,11 +779,24 @@ def peer_signal(done, self_index: int, epoch: int, like: torch.Tensor) -> None:
     for r, t in enumerate(done):
         a.done[r] = t.data_ptr()
     a.n_peers, a.self_, a.epoch = n, self_index, epoch
+    if epoch_base is not None:
+        a.epoch_base = epoch_base.data_ptr()
     lib = load()
-    _issue(CSA_CALL_PEER_SIGNAL, a,
-           lambda st: lib.csa_peer_signal(ctypes.cast(a.done, POINTER(c_void_p)), n, self_index, epoch, st),
-           "csa_peer_signal", _stream_ptr(like))
+    _issue(CSA_CALL_PEER_SIGNAL, a, lambda st: lib.csa_peer_signal_ex(ctypes.byref(a), st), "csa_peer_signal",
+           _stream_ptr(like), like)
     LAUNCHES["csa_peer_signal"] += 1
+
+
+def epoch_advance(epoch_base: torch.Tensor, delta: int) -> None:
+    """``*epoch_base += delta`` on the current stream (see csa_epoch_advance): ends a step whose exchange calls
+    used epochs relative to the device-resident base."""
+    _require_cuda(epoch_base)
+    a = CsaEpochAdvanceArgs()
+    a.epoch_base, a.delta = epoch_base.data_ptr(), delta
+    lib = load()
+    _issue(CSA_CALL_EPOCH_ADVANCE, a, lambda st: lib.csa_epoch_advance(a.epoch_base, a.delta, st),
+           "csa_epoch_advance", _stream_ptr(epoch_base), epoch_base)
+    LAUNCHES["csa_epoch_advance"] += 1
 
 
 def enable_peer_access(peer_device: int) -> None:

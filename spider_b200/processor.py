@@ -250,10 +250,11 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                               k if keep_kv else None, v if keep_kv else None)
             self.id_bank[cur_step] = entry
         else:
-            if self.dist is not None:
-                raise NotImplementedError("read passes are not sharded: run them on a rank that holds the whole "
-                                          "id_bank (spider_b200/dist.py)")
             entry = self.id_bank[cur_step]   # KeyError for a step the write pass never reached (:92)
+            if self.dist is not None and entry.has_kv() and entry.k.shape[0] == self.dist.local_batch * N:
+                # the write pass was sharded: this rank holds the K/V of its own frames only.  Make the entry whole
+                # (all-gather over the ranks, once per layer and step); reads then need no exchange at all.
+                entry.k, entry.v = self.dist.gather_bank(entry.k, entry.v)
             if B != 2 and not (self.batched_read and B > 0 and B % 2 == 0):
                 raise ValueError(f"read pass expects batch 2 (uncond, cond), got {B}"
                                  + ("" if self.batched_read else " (set batched_read=True for 2*R frames)"))
@@ -305,6 +306,8 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
             h.attn_count = 0
             h.cur_step += 1
             native.flush_batch()
+            if self.dist is not None:
+                self.dist.end_step()
             h.mask1024, h.mask4096 = _masks.cal_attn_mask_xl(
                 self.total_length, self.id_length, h.sa32, h.sa64, h.height, h.width,
                 device=self.device, dtype=self.dtype,

@@ -68,8 +68,11 @@ def gather_kv(k, v, group_rows, n_groups, s_idx, s_count, max_rows):
 def attn_fwd(q, o, *, heads, n_groups, n_frames, n_q, k_a=None, v_a=None, a_group_rows=0, k_b=None, v_b=None,
              b_group_rows=0, idx=None, counts=None, list_base=-1, list_step=0, g_adjust=0, ca=(0, 0, 0),
              cb=(0, 0, 0), scale=None, max_ctas=0, ranges=None, range_base=0, range_step=0, split=True,
-             b_first=False, ready=None, ready_epoch=0, ready_bounds=None, ready_peers=0, ready_frames_per_peer=0):
+             b_first=False, ready=None, ready_epoch=0, ready_bounds=None, ready_peers=0, ready_frames_per_peer=0,
+             epoch_base=None):
     C = q.shape[1]
+    if epoch_base is not None:
+        ready_epoch += int(epoch_base[0])
     if ready is not None:
         # the kernel waits per peer when it reaches that peer's rows; the emulation waits for all of them up front
         for r in range(ready_peers if ready_frames_per_peer > 0 else len(ready_bounds) - 1):
@@ -113,7 +116,10 @@ def _wait_ge(flags, i, value, what, timeout=120.0):
 
 
 def peer_scatter_kv(k, v, idx, count, dst_row0, k_dst, v_dst, ready, self_index, epoch, done, done_epoch, counter,
-                    ranges=None, frames_per_peer=0, idx_adjust=0):
+                    ranges=None, frames_per_peer=0, idx_adjust=0, epoch_base=None):
+    if epoch_base is not None:     # epochs in device memory: offsets to the base (done_epoch may be <= 0)
+        epoch += int(epoch_base[0])
+        done_epoch += int(epoch_base[0])
     for r in range(len(k_dst)):
         if r != self_index and done_epoch > 0:
             _wait_ge(done, r, done_epoch, "done")
@@ -132,7 +138,14 @@ def peer_scatter_kv(k, v, idx, count, dst_row0, k_dst, v_dst, ready, self_index,
     PEER_LOG.append(("scatter", epoch, count, dst_row0, done_epoch))
 
 
-def peer_signal(done, self_index, epoch, like):
+def epoch_advance(epoch_base, delta):
+    epoch_base[0] += delta
+    PEER_LOG.append(("advance", delta))
+
+
+def peer_signal(done, self_index, epoch, like, epoch_base=None):
+    if epoch_base is not None:
+        epoch += int(epoch_base[0])
     for r in range(len(done)):
         if r != self_index:
             done[r][self_index] = epoch
@@ -150,7 +163,7 @@ def install(monkeypatch_or_none, native, processor_cls=None):
     """Replace the native entry points by the emulations (monkeypatch fixture, or plain setattr when None)."""
     pairs = dict(compact_rows=compact_rows, sample_ranges=sample_ranges, gather_rows=gather_rows,
                  gather_kv=gather_kv, attn_fwd=attn_fwd, peer_scatter_kv=peer_scatter_kv, peer_signal=peer_signal,
-                 enable_peer_access=enable_peer_access)
+                 enable_peer_access=enable_peer_access, epoch_advance=epoch_advance)
     for name, fn in pairs.items():
         if monkeypatch_or_none is None:
             setattr(native, name, fn)

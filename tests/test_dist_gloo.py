@@ -163,18 +163,120 @@ def test_sharded_write_pass_matches_single_process_and_oracle(world, exchange, m
         assert (nbytes > 0) == (gc > 1)          # G == 2 exchanges nothing
         assert bank_keys == [25, 26, 27]
         if exchange == "p2p" and gc > 1:
-            # one fused scatter + one release signal per consistent layer call; the smaller layer comes first, so the
-            # buffers are allocated twice and the epochs restart with the second allocation
+            # one fused scatter + one release signal per consistent layer call.  Epochs live in device memory: a call
+            # passes its number within the step, the kernels add the base, end_step() advances the base by the (even)
+            # number of calls — an odd step is padded with an epoch that is only released.  The smaller layer comes
+            # first, so the buffers are re-allocated by the second call (epochs restart there: step 0 is 1 | 1 + pad).
             n_calls = STEPS * 2
-            assert [e[0] for e in peer_log] == ["scatter", "signal"] * n_calls
-            assert peer_state == (2, n_calls - 1)
+            real = [e for e in peer_log if e[0] in ("scatter", "signal")]
+            assert [e[0] for e in real] == ["scatter", "signal", "scatter", "signal", "signal"] + \
+                ["scatter", "signal"] * (n_calls - 2)
+            assert [e for e in peer_log if e[0] == "advance"] == [("advance", 2)] * STEPS
+            assert peer_state == (2, 0)
             epochs = [e[1] for e in peer_log if e[0] == "scatter"]
-            assert epochs == [1] + list(range(1, n_calls))
-            # a slot is rewritten only after every peer has released it: done_epoch = epoch - 2
-            assert all(e[4] == max(0, e[1] - 2) for e in peer_log if e[0] == "scatter")
+            assert epochs == [1, 1] + list(range(3, n_calls + 1))
+            assert [e[1] for e in real if e[0] == "signal"] == [1, 1, 2] + list(range(3, n_calls + 1))
+            # a slot is rewritten only after every peer has released it: done_epoch = epoch - 2 (no wait if <= 0)
+            assert all(e[4] == e[1] - 2 for e in peer_log if e[0] == "scatter")
         else:
             assert peer_log == [] and peer_state is None
     assert len(seen) == world
+
+
+def _read_inputs(world):
+    g = torch.Generator().manual_seed(77)
+    return [[[torch.randn((2, n, C), generator=g) for n in (16, 64)] for _ in range(STEPS)] for _ in range(world)]
+
+
+def _run_reads(host, procs, attn, xr):
+    """one generated frame through the read pass of the STEPS written steps (Comic_Generation.py:441-448)"""
+    outs = []
+    host.write, host.cur_step, host.attn_count = False, 25, 0
+    orig = random.random
+    random.random = lambda: 0.5
+    try:
+        with torch.no_grad():
+            for s in range(STEPS):
+                for li, p in enumerate(procs):
+                    outs.append(p(attn, xr[s][li]))
+    finally:
+        random.random = orig
+    return outs
+
+
+def _worker_story(rank, world, port, q, exchange):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    if exchange == "p2p":
+        mp.set_sharing_strategy("file_system")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from spider_b200.dist import FrameSharding
+
+        host = spider_b200.StoryGlobals()
+        host.height, host.width, host.total_count = H, W, 2
+        cls = make_processor_class(host)
+        abi_emulation.install(None, native, cls)
+        sh = FrameSharding(FL, None, torch.device("cpu"), exchange=exchange)
+        procs = [cls(id_length=FL, device="cpu", dtype=torch.float32) for _ in range(2)]
+        for p in procs:
+            p.dist = sh
+        attn, xs = _make_inputs()
+
+        def slicer(x):
+            half = x[sh.cfg * FL:(sh.cfg + 1) * FL]
+            return half[sh.f0:sh.f0 + sh.frames_local].contiguous()
+
+        _run_story(host, procs, attn, xs, slicer)                      # sharded write pass: sharded bank
+        shard_rows = [int(p.id_bank[25].k.shape[0]) for p in procs]
+        outs = _run_reads(host, procs, attn, _read_inputs(world)[rank])  # every rank generates ITS OWN frame
+        whole_rows = [int(p.id_bank[25].k.shape[0]) for p in procs]
+        q.put((rank, [o.numpy().copy() for o in outs], shard_rows, whole_rows))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,exchange", [(2, "nccl"), (4, "p2p")])
+def test_sharded_story_finishes_write_then_frame_parallel_reads(world, exchange, monkeypatch):
+    """An N-GPU story runs to the end: sharded write pass, the sharded id_bank is all-gathered by the first read of
+    each (layer, step) entry, and every rank then generates a different frame — each equal to what the single-process
+    processor produces for that frame from the unsharded bank."""
+    import copy
+
+    host = spider_b200.StoryGlobals()
+    host.height, host.width, host.total_count = H, W, 2
+    cls = make_processor_class(host)
+    abi_emulation.install(monkeypatch, native, None)
+    monkeypatch.setattr(cls, "_check_input", staticmethod(lambda x: None))
+    procs = [cls(id_length=FL, device="cpu", dtype=torch.float32) for _ in range(2)]
+    attn, xs = _make_inputs()
+    _run_story(host, procs, attn, xs, lambda x: x)
+    rng_after_write = torch.get_rng_state()
+    masks_after_write = copy.deepcopy((host.mask1024, host.mask4096))
+    want = []
+    for r in range(world):
+        torch.set_rng_state(rng_after_write)
+        host.mask1024, host.mask4096 = copy.deepcopy(masks_after_write)
+        want.append(_run_reads(host, procs, attn, _read_inputs(world)[r]))
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_story, args=(r, world, port, q, exchange)) for r in range(world)]
+    for p in ps:
+        p.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, outs, shard_rows, whole_rows in results:
+        fr = FL // (world // 2)
+        assert shard_rows == [fr * 16, fr * 64] and whole_rows == [2 * FL * 16, 2 * FL * 64]
+        assert len(outs) == len(want[rank])
+        for got, ref in zip(outs, want[rank]):
+            assert (torch.from_numpy(got) - ref).abs().max().item() < 2e-5
 
 
 def test_sharding_geometry_errors():
