@@ -364,11 +364,15 @@ class Workload:
 
     def flops(self) -> float:
         """algorithmic attention FLOPs of all counted steps, WHOLE job: 4 * d * H * 2 * N * sum_f K_f per layer"""
-        k32, k16 = (int(x) for x in self.kf.tolist())
+        k32, k16 = (int(x) for x in getattr(self, "kf_timed", self.kf).tolist())
         total = 0.0
         for (n, c, h) in self.plan:
             total += 4.0 * HEAD_DIM * h * 2 * n * (k32 if n == self.n32 else k16)
         return total
+
+
+def world_size() -> int:
+    return int(os.environ.get("WORLD_SIZE", "1"))
 
 
 def time_workload(wl, args, steps, warmup, barrier, rank, events=True):
@@ -417,12 +421,28 @@ def time_workload(wl, args, steps, warmup, barrier, rank, events=True):
                 wl.step(count=True)
         e1.record()
         host_issue_ms = (time.perf_counter() - t_host0) * 1e3   # CPU time to ISSUE the steps (no sync inside)
-        barrier()
+        torch.cuda.synchronize()
         ms_total = e0.elapsed_time(e1)
-        clocks = sampler.stop() if sampler else None
+        wl.kf_timed = wl.kf.clone()          # sum K_f of exactly the timed steps
         attn_events = native.ATTN_EVENTS or []
-        native.ATTN_EVENTS = None
         attn_ms = sum(a.elapsed_time(b) for a, b, *_ in attn_events)
+        native.ATTN_EVENTS = None
+        # nvidia-smi samples every ~100 ms and K replayed steps may be over in less: keep the identical load running
+        # (untimed) until the sampler has had ~0.8 s of it, then stop it.  Every rank runs the same number of steps.
+        need = min(400, int(max(0.0, 800.0 - ms_total) / max(ms_total / steps, 0.05)))
+        if world_size() > 1:
+            import torch.distributed as dist
+            t = torch.tensor([need], device=wl.dev, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            need = int(t.item())
+        for _ in range(need):
+            graph.replay() if graph is not None else wl.step(count=False)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        if clocks is not None:
+            clocks["window"] = (f"the {steps} timed steps + {need} identical untimed steps right behind them "
+                                "(nvidia-smi needs ~1 s of load to return samples)")
+        native.ATTN_EVENTS = None
         launches = dict(native.LAUNCHES)
         if graph is not None:
             # the launch counters ran at capture; every replay re-executes exactly those launches

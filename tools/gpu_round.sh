@@ -36,8 +36,20 @@ for w in $WHAT; do
     launches)
       # every launch of one warm step with its device time (cold-cache, serialised: compare SHARES)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv \
-        --log-file "$OUT/launches.csv" python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > "$OUT/launches.log" 2>&1
+        --log-file "$OUT/launches.csv" python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-graph --no-hbm > "$OUT/launches.log" 2>&1
       echo "ncu launches exit $?"
+      ;;
+    f16)
+      timeout 600 python bench.py --frames 16 --steps 5 --warmup 3 --no-cpu --no-e2e --no-hbm --share-weights > "$OUT/bench_f16_n1.json" 2> "$OUT/bench_f16_n1.err"
+      echo "bench F=16 exit $?"; head -c 600 "$OUT/bench_f16_n1.json"; tail -3 "$OUT/bench_f16_n1.err"
+      ;;
+    all70)
+      timeout 600 python bench.py --placement all --steps 5 --warmup 3 --no-cpu --no-hbm > "$OUT/bench_all70.json" 2> "$OUT/bench_all70.err"
+      echo "bench all-70 exit $?"; head -c 600 "$OUT/bench_all70.json"; tail -3 "$OUT/bench_all70.err"
+      ;;
+    sweep)
+      timeout 1200 python tools/sweep_inproc.py --out "$OUT/sweep_n1.md" > "$OUT/sweep_n1.jsonl" 2> "$OUT/sweep_n1.err"
+      echo "sweep exit $?"; tail -60 "$OUT/sweep_n1.md"; tail -3 "$OUT/sweep_n1.err"
       ;;
     sdpa)
       # same-box GPU comparator: the reference call through torch SDPA with the dense mask
@@ -47,7 +59,7 @@ for w in $WHAT; do
     full)
       # one 32x32-class and one 64x64-class attention launch of a warm step
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:csa_attn_kernel -s 136 -c 4 \
-        -o "$OUT/attn_full" -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > "$OUT/full.log" 2>&1
+        -o "$OUT/attn_full" -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-graph --no-hbm > "$OUT/full.log" 2>&1
       echo "ncu full exit $?"; tail -3 "$OUT/full.log"
       ;;
   esac
