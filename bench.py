@@ -273,6 +273,9 @@ def workload_config(args, n_gpus: int):
         "workload": (f"SDXL {args.res}x{args.res} story write pass, {args.frames} frames x2 CFG, one denoise step = "
                      f"{len(plan)} SpatialAttnProcessor2_0 calls ({args.placement}-block attn1 placement), "
                      f"consistent branch, sa32=sa64={args.sa}"),
+        "pass": getattr(args, "pass_", "write"),
+        **({"read_frames": args.read_frames, "batched_read": bool(args.batched_read)}
+           if getattr(args, "pass_", "write") == "read" else {}),
         "frames": args.frames, "cfg": 2, "height": args.res, "width": args.res, "sa": args.sa,
         "layers": len(plan), "placement": args.placement, "gate": "forced consistent (cur_step=25)",
         "parallelism": "single GPU" if n_gpus == 1 else (
@@ -345,11 +348,31 @@ class Workload:
                                                                     device=str(dev), dtype=torch.float16)
         self.kf = torch.zeros(2, dtype=torch.int64, device=dev)   # sum over timed steps of sum_f K_f at /32, /16
         self.steps_counted = 0
+        # --pass read: R generated frames per denoise step attend the id_bank of a write step + themselves
+        # (Comic_Generation.py:441-448): R batch-2 calls per layer as the reference issues them, or ONE call per layer
+        # with batch 2R (opt-in batched_read)
+        self.read = getattr(args, "pass_", "write") == "read"
+        if self.read:
+            if world > 1:
+                raise SystemExit("--pass read is a single-GPU measurement (reads are frame-parallel, no exchange)")
+            R = self.R = args.read_frames
+            with torch.no_grad():
+                self.step(count=False, force_write=True)          # fills id_bank[25] of every layer
+            host.write = False
+            cls.batched_read = bool(args.batched_read)
+            self.hidden_r = []
+            for (n, c, h) in plan:
+                if args.batched_read:
+                    self.hidden_r.append([torch.randn((2 * R, n, c), device=dev, generator=g).to(dtype)])
+                else:
+                    self.hidden_r.append([torch.randn((2, n, c), device=dev, generator=g).to(dtype) for _ in range(R)])
 
-    def step(self, count=True):
+    def step(self, count=True, force_write=False):
         host = self.host
         host.cur_step = 25       # the bank entry of step 25 is overwritten each time (bounded memory)
         host.attn_count = 0
+        if getattr(self, "read", False) and not force_write:
+            return self.step_read(count)
         if count:
             # K_f = N + the two runs of the sampled list frame f attends (ranges[f] = {start1, len1, start2, len2})
             Fl = self.Fl
@@ -362,6 +385,22 @@ class Workload:
             out = p(a, x)
         return out
 
+    def step_read(self, count=True):
+        host, Fl = self.host, self.Fl
+        if count:
+            # every generated frame attends the sampled bank rows (ranges[F] = {0, |S|, 0, 0}) + its own N tokens
+            r32 = host.mask1024.sample_list(self.dev)[2]
+            r16 = host.mask4096.sample_list(self.dev)[2]
+            self.kf[0] += self.R * (r32[Fl, 1] + self.n32)
+            self.kf[1] += self.R * (r16[Fl, 1] + self.n16)
+        out = None
+        for i, (a, p) in enumerate(zip(self.attns, self.procs)):
+            for x in self.hidden_r[i]:
+                host.cur_step = 25
+                out = p(a, x)
+        host.attn_count = 0
+        return out
+
     def flops(self) -> float:
         """algorithmic attention FLOPs of all counted steps, WHOLE job: 4 * d * H * 2 * N * sum_f K_f per layer"""
         k32, k16 = (int(x) for x in getattr(self, "kf_timed", self.kf).tolist())
@@ -369,6 +408,18 @@ class Workload:
         for (n, c, h) in self.plan:
             total += 4.0 * HEAD_DIM * h * 2 * n * (k32 if n == self.n32 else k16)
         return total
+
+
+def bank_report(wl, world):
+    """What the write pass keeps per denoise step (IdBank.nbytes() of every layer after a step) and what a 50-step
+    story would hold, whole job."""
+    per_step = sum(p.id_bank.nbytes() for p in wl.procs) * world
+    store = type(wl.procs[0]).bank_store
+    return {"store": store, "bytes_per_step": per_step, "gb_for_50_steps": round(per_step * 50 / 1e9, 2),
+            "note": ("projected K and V of the identity frames per (layer, step), zero-copy from the K|V GEMM; "
+                     "bank_store='hidden' keeps the layer inputs instead (half the bytes, the reference's layout) and "
+                     "projects only the sampled rows at read time; bank_capacity=N preallocates an arena and raises "
+                     "BankCapacityError beyond it")}
 
 
 def world_size() -> int:
@@ -390,18 +441,24 @@ def time_workload(wl, args, steps, warmup, barrier, rank, events=True):
         if events:
             native.prepare_event_pool(2 * len(wl.plan) * (1 if args.graph else steps) + 8)
         native.ATTN_EVENTS = None
+        graph_ev = None
         if args.graph:
             def instrument():
                 # from here on (the capture) the attention launches are bracketed by event-record nodes
-                native.ATTN_EVENTS = [] if events else None
+                native.ATTN_EVENTS = []
             try:
-                graph = StepGraph(lambda: wl.step(count=True), wl.dev, warmup=1).capture(before_capture=instrument)
+                # the step as ONE graph; and, for the roofline line, a second capture of the same step whose attention
+                # launches sit between event-record nodes — it is replayed as the LAST of the K timed steps
+                graph = StepGraph(lambda: wl.step(count=True), wl.dev, warmup=1).capture()
+                if events:
+                    graph_ev = StepGraph(lambda: wl.step(count=True), wl.dev, warmup=0).capture(
+                        before_capture=instrument)
                 mode = "cuda graph (one cudaGraphLaunch per denoise step)"
             except Exception as e:   # noqa: BLE001 - a driver / torch that cannot capture this step: say so, go eager
                 if rank == 0:
                     print(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {e}); timing eagerly",
                           file=sys.stderr, flush=True)
-                graph = None
+                graph = graph_ev = None
                 native.abort_batch()
                 torch.cuda.synchronize()
         if graph is None:
@@ -413,14 +470,25 @@ def time_workload(wl, args, steps, warmup, barrier, rank, events=True):
         barrier()
         t_host0 = time.perf_counter()
         e0.record()
+        t_host_plain = None
         if graph is not None:
-            for _ in range(steps):
+            for _ in range(steps - (1 if graph_ev is not None else 0)):
                 graph.replay()
+            t_host_plain = time.perf_counter()
+            if graph_ev is not None:
+                graph_ev.replay()
         else:
             for _ in range(steps):
                 wl.step(count=True)
         e1.record()
-        host_issue_ms = (time.perf_counter() - t_host0) * 1e3   # CPU time to ISSUE the steps (no sync inside)
+        t_host1 = time.perf_counter()
+        # CPU time to ISSUE a step (no sync inside): the plain replays; the instrumented last step is reported apart
+        if t_host_plain is not None and graph_ev is not None and steps > 1:
+            host_issue_ms = (t_host_plain - t_host0) * 1e3 / (steps - 1) * steps
+            host_issue_instr_ms = (t_host1 - t_host_plain) * 1e3
+        else:
+            host_issue_ms = (t_host1 - t_host0) * 1e3
+            host_issue_instr_ms = None
         torch.cuda.synchronize()
         ms_total = e0.elapsed_time(e1)
         wl.kf_timed = wl.kf.clone()          # sum K_f of exactly the timed steps
@@ -437,6 +505,7 @@ def time_workload(wl, args, steps, warmup, barrier, rank, events=True):
             need = int(t.item())
         for _ in range(need):
             graph.replay() if graph is not None else wl.step(count=False)
+        del graph_ev
         barrier()
         clocks = sampler.stop() if sampler else None
         if clocks is not None:
@@ -448,7 +517,8 @@ def time_workload(wl, args, steps, warmup, barrier, rank, events=True):
             # the launch counters ran at capture; every replay re-executes exactly those launches
             launches = {k: v * steps for k, v in wl.launches_per_step.items()} if hasattr(wl, "launches_per_step") \
                 else launches
-    return {"ms_total": ms_total, "host_issue_ms": host_issue_ms, "clocks": clocks, "attn_events": len(attn_events),
+    return {"ms_total": ms_total, "host_issue_ms": host_issue_ms, "host_issue_instr_ms": host_issue_instr_ms,
+            "clocks": clocks, "attn_events": len(attn_events),
             "attn_ms": attn_ms, "attn_steps": (1 if graph is not None else steps), "launches": launches,
             "mode": mode, "graph": graph}
 
@@ -535,6 +605,7 @@ def run_b200_arm(args):
                 extra["config4"] = {"frames": 16, "ms_per_step": round(ms4, 4),
                                     "value": round(f4 / (ms4 * 1e-3) / 1e12, 2), "unit": UNIT,
                                     "tflop_per_step": round(f4 / 1e12, 3), "mode": m4["mode"],
+                                    "host_issue_ms_per_step": round(m4["host_issue_ms"] / max(2, args.steps // 3), 3),
                                     "n1_ms_per_step_reference": N1_F16_MS,
                                     "efficiency_vs_n1_ms": round(N1_F16_MS / ms4 / world, 4),
                                     "note": ("strong scaling of the 16-frame 1024^2 story (BASELINE config 4); "
@@ -572,7 +643,10 @@ def run_b200_arm(args):
             "library_gemm_launches": gemm_launches,
             "launches_by_entry": launches,
             "issue": m["mode"],
+            "id_bank": bank_report(wl, world),
             "host_issue_ms_per_step": round(m["host_issue_ms"] / steps, 3),
+            "host_issue_ms_instrumented_step": (round(m["host_issue_instr_ms"], 3)
+                                                if m.get("host_issue_instr_ms") is not None else None),
             "clocks": m["clocks"],
             "roofline": {
                 "kernel": "csa_attn_kernel (tcgen05/TMEM flash attention over compacted keys)",
@@ -582,8 +656,8 @@ def run_b200_arm(args):
                 "frac_of_sustained": (round(achieved / peaks["bf16_tflops_sustained"], 4)
                                       if peaks.get("bf16_tflops_sustained") else None),
                 "launches_timed": m["attn_events"], "avg_launch_ms": round(attn_ms / n_attn, 5),
-                "timed_over": (f"the attention launches of the last of the {steps} timed steps (event-record nodes "
-                               "inside the replayed graph)" if m["attn_steps"] != steps else
+                "timed_over": (f"the attention launches of the last of the {steps} timed steps (that step is replayed "
+                               "from a capture with event-record nodes around them)" if m["attn_steps"] != steps else
                                f"all attention launches of the {steps} timed steps"),
                 "attn_share_of_step": round(attn_ms / (ms_total / steps * m["attn_steps"]), 4),
                 "traffic": load_traffic(),
@@ -835,6 +909,12 @@ def main():
     ap.add_argument("--module-projections", action="store_true",
                     help="project through the attn module's nn.Linear layers instead of the library's batched "
                          "csa_linear calls (A/B of the host overhead)")
+    ap.add_argument("--pass", dest="pass_", choices=["write", "read"], default="write",
+                    help="read: R generated frames per step attend the id_bank of a write step (Comic_Generation.py"
+                         ":441-448) instead of the write pass")
+    ap.add_argument("--read-frames", type=int, default=4, help="--pass read: generated frames per denoise step")
+    ap.add_argument("--batched-read", action="store_true",
+                    help="--pass read: one call per layer with batch 2R (batched_read) instead of R batch-2 calls")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="issue every step call by call from Python instead of replaying one CUDA graph per step")
     ap.add_argument("--no-hbm", action="store_true", help="skip the HBM-bound kernels' roofline entries")

@@ -104,7 +104,7 @@ class SampledBankEntry(list):
     def _materialise(self):
         if self._materialised:
             return
-        n = int(self.count.item())
+        n = self._n_valid if self._n_valid is not None else int(self.count.item())
         pos = self._s_idx[:n].to(torch.int64)
         img = torch.div(pos, self.n_tokens, rounding_mode="floor")
         bounds = torch.searchsorted(img, torch.arange(self.img_nums + 1, device=img.device)).tolist()
@@ -229,10 +229,18 @@ class SpatialAttnProcessorLowVram(torch.nn.Module):
             cm = self._indices(h, N, dev).mask_for(img_nums)
             s_idx, s_count, _ = cm.sample_list(dev)
             cap = img_nums * N
-            packed = torch.empty((2, cap, C), dtype=x.dtype, device=dev)
-            for g in range(2):
-                native.gather_rows(x2, s_idx, cap, row_base=g * cap, count=s_count, out=packed[g])
+            # the bank keeps the SAMPLED tokens only, like the reference (:174-179, `.clone()` of the gathered rows):
+            # exactly `count` rows per CFG half.  The count is read back once per re-sampled mask and shared by all
+            # layers of the step (one host sync per step and resolution).
+            n_valid = getattr(cm, "_n_sampled_host", None)
+            if n_valid is None:
+                n_valid = cm._n_sampled_host = int(s_count.item())
+            packed = torch.empty((2, n_valid, C), dtype=x.dtype, device=dev)
+            if n_valid > 0:
+                for g in range(2):
+                    native.gather_rows(x2, s_idx, n_valid, row_base=g * cap, count=s_count, out=packed[g])
             entry = SampledBankEntry(packed, s_count, img_nums, N, s_idx)
+            entry._n_valid = n_valid
             self.id_bank.setdefault(chars[0], {})[cur_step] = entry
         else:
             if B != 2:

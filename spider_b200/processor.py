@@ -33,6 +33,10 @@ from . import native
 from .bank import STORE_MODES, BankEntry, IdBank
 
 
+class BankCapacityError(RuntimeError):
+    """The preallocated id_bank arena of a layer is full (``bank_capacity`` steps)."""
+
+
 class StoryGlobals:
     """Default host namespace: the reference's module globals (Comic_Generation.py:82-85, :327-349) as attributes.
     ``install()`` binds processors to the reference's own module instead."""
@@ -75,6 +79,12 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                             # (csa_linear) and the whole call handed over in one batch (csa_run_batch) whenever the
                             # attn module is the plain SDXL attn1 shape (bias-free Linear q/k/v, Linear + Dropout(0)
                             # out, no norms); anything else goes through the module's own projections
+    bank_capacity = None    # None: the bank grows step by step like the reference's dict (Comic_Generation.py:89), each
+                            # entry aliasing that step's K|V projection output.  int: a preallocated arena of that
+                            # many steps per layer — the K|V GEMM writes straight into the step's slot, nothing is
+                            # allocated during the write pass, and a step beyond the capacity raises BankCapacityError
+                            # instead of running the device out of memory (1024^2, id_length 4, "kv": 1.76 GB per
+                            # denoise step over the 36 layers, 88 GB for 50 steps; "hidden" halves it)
     inplace_masks = True    # step roll-over re-samples the host's CompactMasks IN PLACE when it can (no allocation,
                             # stable device pointers: a captured denoise step can be replayed, spider_b200/graph.py)
     batched_read = False    # opt-in: a read call may carry R generated frames (batch 2*R, [uncond R,
@@ -183,7 +193,10 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
             try:
                 x2 = x.view(B * N, C)
                 q = native.linear(x2, plan[1])
-                kv = native.linear(x2, plan[2])       # K and V in one GEMM: columns [0, C) and [C, 2C)
+                # K and V in one GEMM: columns [0, C) and [C, 2C) — written straight into the bank arena's slot of
+                # this step when the write pass keeps K/V there
+                slot = self._arena_slot(cur_step, B * N, 2 * C, x) if write and self.bank_capacity else None
+                kv = native.linear(x2, plan[2], out=slot)
                 k, v = kv[:, :C], kv[:, C:]
             except Exception:
                 native.abort_batch()
@@ -198,6 +211,34 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
         except Exception:
             native.abort_batch()
             raise
+
+    def _arena_slot(self, step, rows: int, cols: int, like: torch.Tensor):
+        """K|V buffer ``(rows, 2C)`` of ``step`` inside this layer's preallocated arena (``bank_capacity`` steps), or
+        None when this write pass does not keep K/V.  Allocated once, at the first write call of the layer."""
+        if self.bank_store not in ("kv", "both"):
+            return None
+        cap = int(self.bank_capacity)
+        st = self.__dict__.get("_arena")
+        if st is None or st[0].shape[1:] != (rows, cols) or st[0].dtype != like.dtype or st[0].device != like.device:
+            native.flush_batch()
+            st = self.__dict__["_arena"] = (torch.empty((cap, rows, cols), dtype=like.dtype, device=like.device), {})
+        buf, slots = st
+        i = slots.get(step)
+        if i is None:
+            if len(slots) >= cap:
+                nbytes = buf[0].numel() * buf.element_size()
+                raise BankCapacityError(
+                    f"id_bank arena of this layer holds {cap} steps x {nbytes / 2 ** 20:.0f} MiB (bank_capacity={cap}); "
+                    f"step {step} does not fit — raise bank_capacity, use bank_store='hidden', or clear id_bank")
+            i = slots[step] = len(slots)
+        return buf[i]
+
+    def clear_bank(self) -> None:
+        """Forget every written step (the arena, if any, is kept and reused)."""
+        self.id_bank.clear()
+        st = self.__dict__.get("_arena")
+        if st is not None:
+            st[1].clear()
 
     def _native_plan(self, attn, x):
         """``(key, w_q, w_kv, w_out, b_out)`` when the attn module is the plain SDXL attn1 shape — bias-free Linear
@@ -265,7 +306,7 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
             if write:
                 self._attn_standard(q, k, v, o, B, N, heads)
             else:
-                self._attn_read(attn, entry, q, k, v, o, N, heads, cm=None)
+                self._attn_read(attn, entry, q, k, v, o, N, heads, cm=None, plan=plan)
         else:
             random_number = random.random()                     # :98 — exactly one draw per call
             rand_num = 0.3 if cur_step < 20 else 0.1            # :99-102
@@ -280,7 +321,7 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                                          "(the reference fails with a mask shape error here)")
                     self._attn_write(q, k, v, o, N, heads, cm)
                 else:
-                    self._attn_read(attn, entry, q, k, v, o, N, heads, cm=cm)
+                    self._attn_read(attn, entry, q, k, v, o, N, heads, cm=cm, plan=plan)
             else:
                 branch = "standard"
                 self._attn_standard(q, k, v, o, B, N, heads)    # :118 — bank ignored even when reading
@@ -342,20 +383,48 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                         k_a=k, v_a=v, a_group_rows=Fl * N,
                         idx=idx, counts=counts, list_base=0, list_step=1)
 
-    def _attn_read(self, attn, entry, q, k, v, o, N, heads, cm):
+    def _project_sampled_bank(self, attn, entry, plan, cm, N, q):
+        """``bank_store="hidden"`` read, gather-before-project: the consistent read attends only the SAMPLED bank rows
+        (mask[F*N:], Comic_Generation.py:106-108), so only those — about sa32/sa64 of the 2*F*N rows the reference
+        re-projects on every call (:162-165) — go through to_k|to_v: gather the sampled hidden rows of both CFG
+        halves (csa_gather_rows), one K|V GEMM over them, and the result already IS the K[S], V[S] buffer pair the
+        attention kernel streams (zero tail included: bias-free projections map the zero rows to zero)."""
+        Fl = self.id_length
+        C = q.shape[1]
+        dev = q.device
+        s_idx, s_count, ranges = cm.sample_list(dev)
+        cap = Fl * N + native.CSA_TILE
+        g = torch.zeros((2 * cap, C), dtype=q.dtype, device=dev)
+        for half, hs in enumerate((entry[0], entry[1])):
+            hs = hs.to(device=dev, dtype=q.dtype).reshape(Fl * N, C)
+            native.gather_rows(hs, s_idx, Fl * N, count=s_count, out=g[half * cap:half * cap + Fl * N])
+        if plan is not None:
+            kv = native.linear(g, plan[2])
+            return kv[:, :C], kv[:, C:], cap, ranges
+        return attn.to_k(g), attn.to_v(g), cap, ranges
+
+    def _attn_read(self, attn, entry, q, k, v, o, N, heads, cm, plan=None):
         """Read mode: keys = id_bank rows (all of them for early steps, :94-96; the sampled ones for the consistent
         branch, mask[F*N:], :106-108) + the current frame, per CFG half.  The bank is K/V source A, the current
         projection source B; nothing is concatenated."""
         Fl = self.id_length
         R = q.shape[0] // (2 * N)          # generated frames in this call (1 unless batched_read)
         native.flush_batch()               # entry.kv() may project bank rows with torch: nothing deferred before it
+        own = dict(k_b=k, v_b=v, b_group_rows=R * N, cb=(0, N, N))
+        if (not entry.has_kv() and cm is not None and self.kv_gather == "pre" and cm.shared_sample
+                and entry[0] is not None and entry[1] is not None
+                and tuple(entry[0].shape) == (Fl, N, q.shape[1]) and tuple(entry[1].shape) == (Fl, N, q.shape[1])
+                and getattr(attn.to_k, "bias", None) is None and getattr(attn.to_v, "bias", None) is None):
+            k_s, v_s, cap, ranges = self._project_sampled_bank(attn, entry, plan, cm, N, q)
+            native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=R, n_q=N,
+                            k_a=k_s, v_a=v_s, a_group_rows=cap, ranges=ranges, range_base=Fl, range_step=0, **own)
+            return
         kb, vb = entry.kv(attn, device=q.device)
         if kb.shape[0] != 2 * Fl * N or kb.shape[1] != q.shape[1]:
             raise ValueError(f"id_bank entry has K/V of shape {tuple(kb.shape)}, expected {(2 * Fl * N, q.shape[1])}")
         if kb.dtype != q.dtype:
             kb, vb = kb.to(q.dtype), vb.to(q.dtype)
         # every generated frame r attends the same bank keys + its own block [r*N, (r+1)*N) of the current projection
-        own = dict(k_b=k, v_b=v, b_group_rows=R * N, cb=(0, N, N))
         if cm is None:
             native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=R, n_q=N,
                             k_a=kb, v_a=vb, a_group_rows=Fl * N, ca=(0, 0, Fl * N), **own)

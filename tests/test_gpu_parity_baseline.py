@@ -198,3 +198,54 @@ def test_f16_all_units_of_one_cfg_half_vs_oracle_gathered():
         e, c = _assert_close(got[rs], want[rs], f"F=16 frame {f}")
         worst = (max(worst[0], e), min(worst[1], c))
     print(f"F=16 all 16 units of the cond half: worst max-abs {worst[0]:.3e} cos {worst[1]:.6f}")
+
+
+def test_bank_arena_capacity_and_equivalence():
+    """bank_capacity=N: the K|V GEMM of a write step lands in a preallocated arena slot (same results as the growing
+    bank, bit for bit), a step beyond the capacity raises instead of allocating, clear_bank() frees the slots."""
+    from spider_b200.processor import BankCapacityError
+
+    H = W = 256
+    Fl, N, C, heads = 4, 64, 1280, 20
+    torch.manual_seed(2)
+    attn = FakeAttention(C, heads).to(DEV, torch.bfloat16)
+    xs = [torch.randn(2 * Fl, N, C, device=DEV, dtype=torch.bfloat16) for _ in range(3)]
+    xr = torch.randn(2, N, C, device=DEV, dtype=torch.bfloat16)
+    outs = {}
+    real = random.random
+    random.random = lambda: 0.99
+    try:
+        for cap in (None, 2):
+            host = spider_b200.StoryGlobals()
+            host.height, host.width, host.total_count = H, W, 10 ** 9
+            torch.cuda.manual_seed(9)
+            host.mask1024, host.mask4096 = spider_b200.cal_attn_mask_xl(Fl + 1, Fl, 0.5, 0.5, H, W, device=DEV)
+            cls = make_processor_class(host)
+            cls.bank_capacity = cap
+            p = cls(id_length=Fl, device=DEV)
+            with torch.no_grad():
+                host.write = True
+                res = []
+                for s in range(2):
+                    host.cur_step = 25 + s
+                    res.append(p(attn, xs[s]))
+                if cap is not None:
+                    host.cur_step = 27
+                    with pytest.raises(BankCapacityError):
+                        p(attn, xs[2])
+                    native.abort_batch()
+                    assert p.id_bank[25].k.data_ptr() == p._arena[0][0].data_ptr()
+                host.write = False
+                for s in range(2):
+                    host.cur_step = 25 + s
+                    res.append(p(attn, xr))
+                if cap is not None:
+                    p.clear_bank()
+                    host.write, host.cur_step = True, 27
+                    p(attn, xs[2])                       # fits again
+            torch.cuda.synchronize()
+            outs[cap] = res
+    finally:
+        random.random = real
+    for a, b in zip(outs[None], outs[2]):
+        assert torch.equal(a, b)
