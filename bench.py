@@ -308,6 +308,8 @@ class Workload:
         host.write = True
         cls = make_processor_class(host)
         cls.native_projections = not args.module_projections
+        cls.native_gemm = args.projections != "cublaslt"
+        cls.gemm_qo = args.projections == "own"
         self.sharding = None
         units_local = 2 * Fl
         if world > 1:
@@ -915,6 +917,9 @@ def main():
     ap.add_argument("--read-frames", type=int, default=4, help="--pass read: generated frames per denoise step")
     ap.add_argument("--batched-read", action="store_true",
                     help="--pass read: one call per layer with batch 2R (batched_read) instead of R batch-2 calls")
+    ap.add_argument("--projections", choices=["own", "mixed", "cublaslt"], default="own",
+                    help="own: every projection on the hand-written sm_100a GEMM (K|V with the fused gather); mixed: "
+                         "only K|V (q / out on cuBLASLt); cublaslt: library GEMMs + csa_gather_kv (round-1 path)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="issue every step call by call from Python instead of replaying one CUDA graph per step")
     ap.add_argument("--no-hbm", action="store_true", help="skip the HBM-bound kernels' roofline entries")

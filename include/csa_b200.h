@@ -332,6 +332,49 @@ typedef struct csa_linear_args {
 int csa_linear(const csa_linear_args_t* args, void* stream);
 
 /*
+ * The same projections as a HAND-WRITTEN sm_100a GEMM (csrc/gemm_sm100.cu: TMA-fed 5-stage ring, tcgen05.mma M128 N128
+ * K16 with two TMEM accumulators, epilogue in registers):  y = alpha * x w^T (+ bias), layouts as csa_linear.  Shapes of
+ * the path only: N % 128 == 0 and K % 64 == 0 (csa_gemm_supported); anything else stays with csa_linear.
+ *
+ * Fused K/V gather (optional, the write pass of the consistent branch, Comic_Generation.py:164-165 feeding :175-177):
+ * when x holds `m / scatter_group_rows` groups (CFG halves) of key rows and w = [w_k; w_v] (n = 2C, split_col = C),
+ * every output row r whose position in the sampled key list S is known —  pos = scatter_pos[r % scatter_group_rows]
+ * >= 0, from csa_sample_positions — is ALSO stored into the S-ordered buffers the attention kernel streams:
+ *     scatter_k[(g * scatter_dst_group_rows + pos) * scatter_ld + c]      = y[r][c]              c <  split_col
+ *     scatter_v[(g * scatter_dst_group_rows + pos) * scatter_ld + c - C]  = y[r][c]              c >= split_col
+ * which replaces the separate csa_gather_kv launch and its second pass over K and V.
+ */
+typedef struct csa_gemm_args {
+  uint32_t struct_size; /* sizeof(csa_gemm_args_t), checked */
+  int32_t dtype;        /* CSA_DTYPE_* of x, w, bias and y */
+  int64_t m, n, k;
+  const void* x;
+  int64_t ldx;
+  const void* w;
+  int64_t ldw;
+  const void* bias; /* NULL = none */
+  void* y;
+  int64_t ldy;
+  float alpha;
+  int32_t _pad0;
+  const int32_t* scatter_pos; /* NULL = no fused gather; device int32[scatter_group_rows] */
+  void* scatter_k;
+  void* scatter_v;
+  int64_t scatter_ld; /* elements */
+  int32_t scatter_group_rows;
+  int32_t scatter_dst_group_rows;
+  int32_t split_col;
+  int32_t _pad1;
+} csa_gemm_args_t;
+
+int csa_gemm(const csa_gemm_args_t* args, void* stream);
+int csa_gemm_supported(int64_t m, int64_t n, int64_t k); /* 1 / 0 */
+
+/* pos[c] = i if s_idx[i] == c for some i < *s_count, else -1, for c in [0, n_cols): the inverse of an ascending index
+ * list (csa_compact_rows output), what the fused gather of csa_gemm looks rows up in. */
+int csa_sample_positions(const int32_t* s_idx, const int32_t* s_count, int32_t n_cols, int32_t* pos, void* stream);
+
+/*
  * One processor call = one call into the library: the entries are executed in order on `stream` (projections, K/V
  * gather or peer exchange, attention, output projection), stopping at the first failure (*failed_index = its
  * position, -1 if none; may be NULL).  Purely a host-overhead device: the launches are the ones the single entry
@@ -345,6 +388,7 @@ int csa_linear(const csa_linear_args_t* args, void* stream);
 #define CSA_CALL_PEER_SIGNAL 5
 #define CSA_CALL_EVENT_RECORD 6
 #define CSA_CALL_EPOCH_ADVANCE 7
+#define CSA_CALL_GEMM 8
 
 typedef struct csa_gather_kv_args { /* the arguments of csa_gather_kv, in its order */
   const void* k;

@@ -1,0 +1,407 @@
+// Hand-written projection GEMM for B200 (sm_100a):  y[M,N] = alpha * x[M,K] w[N,K]^T (+ bias[N]), 16-bit in/out, fp32
+// accumulation in TMEM — the projections either side of the attention (attn.to_q / to_k|to_v / to_out[0] of diffusers'
+// Attention module, StoryDiffusion/Comic_Generation.py:155,164-165,185) with torch's nn.Linear layouts, so the weights
+// are read where the module keeps them (both operands are K-major: exactly the Q K^T operand shape of the attention
+// kernel).  Replaces the cuBLASLt calls of csa_linear for the shapes of the path (K % 64 == 0, N % 128 == 0).
+//
+// Persistent CTAs (one per SM, 192 threads) in CLUSTERS OF TWO, warp-specialised:
+//   warp 0      TMA producer: per 64-wide k-block its own 128 x 64 tile of x, and HALF of the BN x 64 tile of w,
+//               multicast to both CTAs of the cluster (the two CTAs work on vertically adjacent output tiles, i.e.
+//               the same rows of w).  With 128 x 128 tiles and no sharing the kernel is bound by the L2 -> SM fabric
+//               (32 KB of operands per 256 tensor-clocks and SM = 3x the ~6300 B/clk the L2 delivers chip-wide:
+//               measured 11.4 TB/s of operand traffic, 730 TFLOP/s); 128 x 256 tiles with the w tile shared need
+//               64 B/clk per SM.
+//   warp 1      TMEM allocator + MMA issue: tcgen05.mma kind::f16, M128 N{256,128} K16, four per k-block; two
+//               accumulators (2 x BN TMEM columns) so that the epilogue of tile i overlaps the main loop of i+1.
+//               A stage is released to BOTH producers of the cluster (multicast commit): the peer writes into it too.
+//   warps 2-5   epilogue: tcgen05.ld (thread == output row), alpha / bias, 16-bit pack, 16-byte stores; and the FUSED
+//               K/V GATHER of the consistent-attention write pass: a row whose position in the sampled key list S is
+//               known (`scatter_pos[row] >= 0`, csa_sample_positions) is also stored, in S order, into the K[S] / V[S]
+//               buffer pair the attention kernel streams — the separate csa_gather_kv launch and its re-read of K and V
+//               from HBM disappear (2.3 % of the denoise step).
+// Tile pairs are dealt round-robin to the clusters, n fastest: clusters that run at the same time share their x
+// tiles through L2.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
+#include "ptx.cuh"
+#include "csa_internal.h"
+
+namespace csa {
+
+constexpr int kGM = 128, kGK = 64;
+constexpr int kGTileA = kGM * kGK * 2;  // 16 KB
+constexpr int kGThreads = 192;
+constexpr int kGSmemBudget = 196608;    // operand ring
+
+template <int kBN>
+struct GemmCfg {
+  static constexpr int kTileB = kBN * kGK * 2;
+  static constexpr int kStages = kGSmemBudget / (kGTileA + kTileB);   // 4 (BN = 256) or 6 (BN = 128)
+};
+
+template <int kBN>
+struct __align__(1024) GemmSmem {
+  uint8_t a[GemmCfg<kBN>::kStages][kGTileA];
+  uint8_t b[GemmCfg<kBN>::kStages][GemmCfg<kBN>::kTileB];
+  uint64_t full[GemmCfg<kBN>::kStages], empty[GemmCfg<kBN>::kStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+struct GemmParams {
+  CUtensorMap tm_x, tm_w;
+  void* y;
+  int64_t ldy;
+  const void* bias;
+  float alpha;
+  int32_t m, n, k;
+  int32_t pairs_m, tiles_n;     // work items: (pair of vertically adjacent 128-row blocks, n tile)
+  // fused gather of the sampled rows (optional)
+  const int32_t* scatter_pos;   // [scatter_group_rows]: position of a row in S, or -1
+  void* scatter_k;              // K[S]: rows g * scatter_dst_group_rows + pos, columns [0, split_col)
+  void* scatter_v;              // V[S]: same rows, columns [split_col, n) shifted down by split_col
+  int64_t scatter_ld;
+  int32_t scatter_group_rows, scatter_dst_group_rows, split_col;
+  uint32_t* dbg;
+};
+
+#define GSB(field) (sb + static_cast<uint32_t>(offsetof(Smem, field)))
+
+template <bool kBF16, int kBN, int kCl>
+__global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << kCl) - 1u);
+  using Smem = GemmSmem<kBN>;
+  constexpr int kStages = GemmCfg<kBN>::kStages;
+  constexpr int kTileB = GemmCfg<kBN>::kTileB;
+  extern __shared__ uint8_t smem_raw[];
+  // the dynamic shared-memory window starts at the same offset in both CTAs of the cluster, so rounding it up gives
+  // the same offsets too (multicast loads and commits address the peer by offset)
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sb = smem_u32(&sm);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();          // which 128-row block of the cluster's kCl
+  const int cluster_id = blockIdx.x / kCl;
+  const int n_clusters = gridDim.x / kCl;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tm_x);
+    tma_prefetch_desc(&p.tm_w);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(GSB(full) + 8u * i, 1);
+      mbar_init(GSB(empty) + 8u * i, kCl);  // every MMA warp of the cluster has consumed the stage
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(GSB(acc_full) + 8u * i, 1);
+      mbar_init(GSB(acc_empty) + 8u * i, 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<2 * kBN>(GSB(tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();    // the peer's barriers exist before anything of ours can reach them
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  const int n_items = p.pairs_m * p.tiles_n;
+  const int kblocks = p.k / kGK;
+
+  if (warp == 0) {
+    // ================================================================================================ producer
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = cluster_id; t < n_items; t += n_clusters) {
+        const int m0 = ((t / p.tiles_n) * kCl + static_cast<int>(crank)) * kGM, n0 = (t % p.tiles_n) * kBN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(GSB(empty) + 8u * st, ph ^ 1, 0x500, p.dbg);
+          mbar_arrive_expect_tx(GSB(full) + 8u * st, kGTileA + kTileB);   // x tile + every slice of the w tile
+          tma_load_2d(&p.tm_x, GSB(a) + static_cast<uint32_t>(kGTileA) * st, GSB(full) + 8u * st, kb * kGK, m0);
+          // my slice of the w tile (rows [n0 + rank * BN/kCl, + BN/kCl)) goes to every CTA, at the slice's place
+          tma_load_2d_mc(&p.tm_w, GSB(b) + static_cast<uint32_t>(kTileB) * st + crank * (kTileB / kCl),
+                         GSB(full) + 8u * st, kb * kGK, n0 + static_cast<int>(crank) * (kBN / kCl), kMask);
+          if (++st == kStages) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================================================ MMA issue
+    constexpr uint32_t idesc = make_idesc(kGM, kBN, kBF16 ? 1 : 0, 0, 0);
+    int st = 0;
+    uint32_t ph = 0, aph[2] = {0, 0};
+    int it = 0;
+    for (int t = cluster_id; t < n_items; t += n_clusters, ++it) {
+      const int buf = it & 1;
+      // the epilogue has drained this accumulator (first use of each buffer: nothing to wait for)
+      if (it >= 2) {
+        mbar_wait(GSB(acc_empty) + 8u * buf, aph[buf], 0x510 + buf, p.dbg);
+        aph[buf] ^= 1;
+      }
+      tc_fence_after();
+      const uint32_t tacc = tmem + buf * kBN;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(GSB(full) + 8u * st, ph, 0x520, p.dbg);
+        tc_fence_after();
+        const uint64_t da = make_sw128_desc(GSB(a) + static_cast<uint32_t>(kGTileA) * st);
+        const uint64_t db = make_sw128_desc(GSB(b) + static_cast<uint32_t>(kTileB) * st);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < kGK / 16; ++kk) mma_ss(tacc, da + kk * 2, db + kk * 2, idesc, (kb | kk) ? 1u : 0u);
+          tc_commit_mc(GSB(empty) + 8u * st, kMask);  // free the stage in every CTA of the cluster
+          if (kb == kblocks - 1) tc_commit(GSB(acc_full) + 8u * buf);
+        }
+        __syncwarp();
+        if (++st == kStages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ================================================================================================ epilogue
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t fph[2] = {0, 0};
+    int it = 0;
+    for (int t = cluster_id; t < n_items; t += n_clusters, ++it) {
+      const int buf = it & 1;
+      const int m0 = ((t / p.tiles_n) * kCl + static_cast<int>(crank)) * kGM, n0 = (t % p.tiles_n) * kBN;
+      const int row = m0 + row_in_tile;
+      const bool row_ok = row < p.m;
+      mbar_wait(GSB(acc_full) + 8u * buf, fph[buf], 0x530 + buf, p.dbg);
+      fph[buf] ^= 1;
+      tc_fence_after();
+      uint16_t* yrow = reinterpret_cast<uint16_t*>(p.y) + static_cast<int64_t>(row) * p.ldy + n0;
+      // fused gather: where this row goes in K[S] / V[S] (or nowhere)
+      int pos = -1, g = 0;
+      if (p.scatter_pos != nullptr && row_ok) {
+        g = row / p.scatter_group_rows;
+        pos = __ldg(p.scatter_pos + (row - g * p.scatter_group_rows));
+      }
+#pragma unroll 1
+      for (int c = 0; c < kBN / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld32(tmem + lane_base + buf * kBN + c * 32, acc);
+        tc_wait_ld();
+        float bv[32];
+        if (p.bias != nullptr) {
+          const uint4* bp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias) + n0 + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 w4 = __ldg(bp + i);
+            const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if constexpr (kBF16) {
+                bv[8 * i + 2 * j] = __uint_as_float(ws[j] << 16);
+                bv[8 * i + 2 * j + 1] = __uint_as_float(ws[j] & 0xffff0000u);
+              } else {
+                const __half2 h2 = *reinterpret_cast<const __half2*>(&ws[j]);
+                bv[8 * i + 2 * j] = __low2float(h2);
+                bv[8 * i + 2 * j + 1] = __high2float(h2);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) bv[i] = 0.f;
+        }
+        uint4 out[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float v0 = fmaf(__uint_as_float(acc[8 * i + 2 * j]), p.alpha, bv[8 * i + 2 * j]);
+            const float v1 = fmaf(__uint_as_float(acc[8 * i + 2 * j + 1]), p.alpha, bv[8 * i + 2 * j + 1]);
+            w[j] = pack2<kBF16>(v0, v1);
+          }
+          out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(yrow + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = out[i];
+          if (pos >= 0) {
+            const int col = n0 + c * 32;                 // a 32-column chunk never straddles split_col (% 128 == 0)
+            const bool is_v = col >= p.split_col;
+            uint4* sd = reinterpret_cast<uint4*>(
+                reinterpret_cast<uint16_t*>(is_v ? p.scatter_v : p.scatter_k) +
+                (static_cast<int64_t>(g) * p.scatter_dst_group_rows + pos) * p.scatter_ld + (col - (is_v ? p.split_col : 0)));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sd[i] = out[i];
+          }
+        }
+      }
+      // this accumulator may be overwritten by the main loop of the tile after next
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(GSB(acc_empty) + 8u * buf);
+    }
+  }
+
+  __syncthreads();
+  cluster_sync_all();    // nobody leaves while its peer may still multicast into it or arrive on its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * kBN>(tmem);
+  }
+}
+
+static int gemm_encode(CUtensorMap* tm, int dtype, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                       uint32_t box_rows) {
+  PFN_encodeTiled fn = get_encode_tiled();
+  if (!fn) return set_error(CSA_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {kGK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, dtype == CSA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(static_cast<int>(r), "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+__global__ void sample_positions_kernel(const int32_t* __restrict__ s_idx, const int32_t* __restrict__ s_count,
+                                        int32_t n_cols, int32_t* __restrict__ pos) {
+  // pos[c] = i if s_idx[i] == c (i < count), else -1.  The list is ascending: every column has one writer.
+  const int count = min(*s_count, n_cols);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cols; i += gridDim.x * blockDim.x) {
+    // binary search of column i in the list
+    int lo = 0, hi = count;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(s_idx + mid) < i) lo = mid + 1; else hi = mid;
+    }
+    pos[i] = (lo < count && __ldg(s_idx + lo) == i) ? lo : -1;
+  }
+}
+
+}  // namespace csa
+
+using namespace csa;
+
+extern "C" int csa_gemm_supported(int64_t m, int64_t n, int64_t k) {
+  return (m > 0 && n > 0 && k > 0 && (n % 128) == 0 && (k % kGK) == 0 && m < (1ll << 30) && n < (1ll << 30)) ? 1 : 0;
+}
+
+template <int kBN, int kCl>
+static int gemm_launch(const csa_gemm_args_t* a, GemmParams& p, int dev, int sms, void* stream) {
+  int rc;
+  if ((rc = gemm_encode(&p.tm_x, a->dtype, a->x, a->m, a->k, a->ldx, kGM))) return rc;
+  if ((rc = gemm_encode(&p.tm_w, a->dtype, a->w, a->n, a->k, a->ldw, kBN / kCl))) return rc;
+  p.pairs_m = static_cast<int32_t>((a->m + kCl * kGM - 1) / (kCl * kGM));
+  p.tiles_n = static_cast<int32_t>(a->n / kBN);
+  const int n_items = p.pairs_m * p.tiles_n;
+  const size_t smem = sizeof(GemmSmem<kBN>) + 1024;
+  auto kern = a->dtype == CSA_DTYPE_BF16 ? csa_gemm_kernel<true, kBN, kCl> : csa_gemm_kernel<false, kBN, kCl>;
+  static bool smem_set[64][2];
+  static int max_clusters[64][2];
+  const int ki = a->dtype == CSA_DTYPE_BF16 ? 1 : 0;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kGThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (dev < 0 || dev >= 64 || !smem_set[dev][ki]) {
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (ce != cudaSuccess)
+      return set_error(static_cast<int>(ce), "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(ce));
+    // how many clusters of this size the device can hold at once (GPC boundaries may strand a few SMs)
+    int nc = sms / kCl;
+    cfg.gridDim = dim3(static_cast<unsigned>(nc * kCl), 1, 1);
+    int q = 0;
+    if (cudaOccupancyMaxActiveClusters(&q, kern, &cfg) == cudaSuccess && q > 0 && q < nc) nc = q;
+    cudaGetLastError();
+    if (dev >= 0 && dev < 64) {
+      smem_set[dev][ki] = true;
+      max_clusters[dev][ki] = nc;
+    }
+  }
+  const int cap = (dev >= 0 && dev < 64) ? max_clusters[dev][ki] : sms / kCl;
+  const int clusters = n_items < cap ? n_items : cap;
+  cfg.gridDim = dim3(static_cast<unsigned>(clusters * kCl), 1, 1);
+  cudaError_t ce = cudaLaunchKernelEx(&cfg, kern, p);
+  if (ce != cudaSuccess) return set_error(static_cast<int>(ce), "csa_gemm_kernel launch: %s", cudaGetErrorString(ce));
+  return 0;
+}
+
+extern "C" int csa_gemm(const csa_gemm_args_t* a, void* stream) {
+  if (!a) return set_error(CSA_E_BADARG, "csa_gemm: null args");
+  if (a->struct_size != sizeof(csa_gemm_args_t))
+    return set_error(CSA_E_BADARG, "csa_gemm: struct_size %u != %zu (ABI mismatch)", a->struct_size,
+                     sizeof(csa_gemm_args_t));
+  if (a->dtype != CSA_DTYPE_F16 && a->dtype != CSA_DTYPE_BF16) return set_error(CSA_E_BADARG, "csa_gemm: dtype %d", a->dtype);
+  if (!csa_gemm_supported(a->m, a->n, a->k))
+    return set_error(CSA_E_SHAPE, "csa_gemm: needs N %% 128 == 0 and K %% 64 == 0, got M=%lld N=%lld K=%lld",
+                     (long long)a->m, (long long)a->n, (long long)a->k);
+  if (a->ldx < a->k || a->ldw < a->k || a->ldy < a->n || ((a->ldx | a->ldw | a->ldy) & 7))
+    return set_error(CSA_E_BADARG, "csa_gemm: leading dimensions must cover the rows and be multiples of 8 elements");
+  if (!a->x || !a->w || !a->y) return set_error(CSA_E_BADARG, "csa_gemm: null pointer");
+  if ((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->w) | reinterpret_cast<uintptr_t>(a->y) |
+       reinterpret_cast<uintptr_t>(a->bias)) & 15)
+    return set_error(CSA_E_BADARG, "csa_gemm: pointers must be 16-byte aligned");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.y = a->y;
+  p.ldy = a->ldy;
+  p.bias = a->bias;
+  p.alpha = a->alpha;
+  p.m = static_cast<int32_t>(a->m);
+  p.n = static_cast<int32_t>(a->n);
+  p.k = static_cast<int32_t>(a->k);
+  if (a->scatter_pos != nullptr) {
+    if (!a->scatter_k || !a->scatter_v || a->scatter_group_rows <= 0 || a->scatter_dst_group_rows <= 0 ||
+        a->split_col <= 0 || (a->split_col % 128) || a->split_col > a->n || (a->scatter_ld & 7) ||
+        ((reinterpret_cast<uintptr_t>(a->scatter_k) | reinterpret_cast<uintptr_t>(a->scatter_v)) & 15) ||
+        (a->m % a->scatter_group_rows))
+      return set_error(CSA_E_BADARG, "csa_gemm: bad scatter arguments (split_col must be a multiple of 128, M a "
+                                     "multiple of scatter_group_rows, buffers 16-byte aligned)");
+    p.scatter_pos = a->scatter_pos;
+    p.scatter_k = a->scatter_k;
+    p.scatter_v = a->scatter_v;
+    p.scatter_ld = a->scatter_ld;
+    p.scatter_group_rows = a->scatter_group_rows;
+    p.scatter_dst_group_rows = a->scatter_dst_group_rows;
+    p.split_col = a->split_col;
+  }
+  p.dbg = debug_record_devptr();
+  int dev = 0;
+  cudaError_t ce = cudaGetDevice(&dev);
+  if (ce != cudaSuccess) return set_error(static_cast<int>(ce), "cudaGetDevice: %s", cudaGetErrorString(ce));
+  const int sms = sm_count(dev);
+  if (sms <= 1) return set_error(CSA_E_DEVICE, "csa_gemm: device %d is not sm_100", dev);
+  // 128 x 256 tiles halve the operand traffic per FLOP; 128 x 128 when N is not a multiple of 256 (N = 640) or when
+  // the wider tile would leave most of the chip without work
+  const int64_t blocks_m = (a->m + kGM - 1) / kGM;
+  const bool wide = (a->n % 256) == 0 && blocks_m * (a->n / 256) >= sms / 2;
+  // CSA_GEMM_CLUSTER=4: four CTAs stacked along M share one w tile instead of two (tuning knob; measured no faster on
+  // any shape of the path — 132 instead of 148 SMs can hold clusters of four — profiles/r02_gemm.md)
+  static const int cl_env = []() {
+    const char* e = getenv("CSA_GEMM_CLUSTER");
+    return e ? atoi(e) : 0;
+  }();
+  const bool four = cl_env == 4;
+  if (wide) return four ? gemm_launch<256, 4>(a, p, dev, sms, stream) : gemm_launch<256, 2>(a, p, dev, sms, stream);
+  return four ? gemm_launch<128, 4>(a, p, dev, sms, stream) : gemm_launch<128, 2>(a, p, dev, sms, stream);
+}
+
+extern "C" int csa_sample_positions(const int32_t* s_idx, const int32_t* s_count, int32_t n_cols, int32_t* pos,
+                                    void* stream) {
+  if (!s_idx || !s_count || !pos || n_cols <= 0) return set_error(CSA_E_BADARG, "csa_sample_positions: bad arguments");
+  const int block = 256;
+  int grid = (n_cols + block - 1) / block;
+  if (grid > 148 * 4) grid = 148 * 4;
+  sample_positions_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(s_idx, s_count, n_cols, pos);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(static_cast<int>(e), "sample_positions_kernel: %s", cudaGetErrorString(e));
+  return 0;
+}

@@ -147,6 +147,7 @@ extern "C" int csa_run_batch(const csa_call_t* calls, int32_t n_calls, void* str
     const void* a = calls[i].args;
     switch (calls[i].kind) {
       case CSA_CALL_LINEAR: rc = csa_linear(static_cast<const csa_linear_args_t*>(a), stream); break;
+      case CSA_CALL_GEMM: rc = csa_gemm(static_cast<const csa_gemm_args_t*>(a), stream); break;
       case CSA_CALL_ATTN: rc = csa_attn_fwd(static_cast<const csa_attn_args_t*>(a), stream); break;
       case CSA_CALL_GATHER_KV: {
         const csa_gather_kv_args_t* g = static_cast<const csa_gather_kv_args_t*>(a);

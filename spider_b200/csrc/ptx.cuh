@@ -96,6 +96,16 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint32_t dst, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(col), "r"(row)
       : "memory");
 }
+// 2-D tiled load, multicast to every CTA of the cluster whose bit is set in `cta_mask`: the tile lands at the same
+// shared-memory offset in each of them and each one's mbarrier (same offset) receives the byte count.
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* m, uint32_t dst, uint32_t bar, int col, int row,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(col), "r"(row), "h"(cta_mask)
+      : "memory");
+}
 // gather4: four rows {r0..r3} of the 2-D tensor, each `box[0]` columns wide starting at `col`, land as four
 // consecutive rows at dst.
 __device__ __forceinline__ void tma_gather4(const CUtensorMap* m, uint32_t dst, uint32_t bar, int col, int r0, int r1,
@@ -142,6 +152,23 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 // Arrive on an mbarrier once every tcgen05 operation issued so far by this thread has completed.
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// Same, arriving on the mbarrier at this offset in EVERY CTA of `cta_mask` (a pipeline stage that a multicast load
+// fills in several CTAs may be refilled only when all of them have consumed it).
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // D[tmem] (+)= A[smem] * B[smem]

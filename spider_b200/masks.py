@@ -39,6 +39,7 @@ class CompactMask:
         self._lists: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
         self._sample_list = None      # (s_idx, s_count, ranges) — see sample_list()
         self._rand = None             # resample_(): the uniform draws the sample vector is thresholded from
+        self._sample_pos = None       # sample_positions(): inverse of the sampled list (fused gather of csa_gemm)
         self.shared_sample = sample is not None   # rows are (S u own block) by construction; dense: checked
 
     # what the reference's mask tensor exposes and drivers may look at
@@ -97,6 +98,14 @@ class CompactMask:
             self._sample_list = (s_idx.view(-1), s_count, ranges)
         return self._sample_list
 
+    def sample_positions(self, device=None) -> torch.Tensor:
+        """``pos [F*N] int32``: position of every key column < F*N in the sampled list S, or -1 — what the K|V
+        projection's epilogue (``csa_gemm``) looks a row up in to store it straight into K[S] / V[S]."""
+        if self._sample_pos is None:
+            s_idx, s_count, _ = self.sample_list(device)
+            self._sample_pos = native.sample_positions(s_idx, s_count, self.id_length * self.n_tokens)
+        return self._sample_pos
+
     def resample_(self, sa: float, dtype=torch.float16, post_sample=None) -> "CompactMask":
         """Draw a fresh sample vector INTO the buffers this mask already owns and refresh, in place, whichever index
         lists were built from the old one — what ``cal_attn_mask_xl`` does at every step roll-over
@@ -124,6 +133,8 @@ class CompactMask:
             s_idx, s_count, ranges = self._sample_list
             native.compact_rows(self._sample, 1, F * N, 0, idx=s_idx.view(1, -1), counts=s_count)
             native.sample_ranges(s_idx, s_count, N, F, out=ranges)
+            if self._sample_pos is not None:
+                native.sample_positions(s_idx, s_count, F * N, out=self._sample_pos)
         self._shard_plan = None   # per-rank run lengths read back from the old sample are stale
         return self
 

@@ -51,6 +51,9 @@ EXPORTED_SYMBOLS = (
     "csa_ipc_open",
     "csa_ipc_close",
     "csa_linear",
+    "csa_gemm",
+    "csa_gemm_supported",
+    "csa_sample_positions",
     "csa_run_batch",
 )
 
@@ -166,6 +169,35 @@ class CsaLinearArgs(ctypes.Structure):
     ]
 
 
+class CsaGemmArgs(ctypes.Structure):
+    """Mirror of ``csa_gemm_args_t``."""
+
+    _fields_ = [
+        ("struct_size", c_uint32),
+        ("dtype", c_int32),
+        ("m", c_int64),
+        ("n", c_int64),
+        ("k", c_int64),
+        ("x", c_void_p),
+        ("ldx", c_int64),
+        ("w", c_void_p),
+        ("ldw", c_int64),
+        ("bias", c_void_p),
+        ("y", c_void_p),
+        ("ldy", c_int64),
+        ("alpha", c_float),
+        ("_pad0", c_int32),
+        ("scatter_pos", c_void_p),
+        ("scatter_k", c_void_p),
+        ("scatter_v", c_void_p),
+        ("scatter_ld", c_int64),
+        ("scatter_group_rows", c_int32),
+        ("scatter_dst_group_rows", c_int32),
+        ("split_col", c_int32),
+        ("_pad1", c_int32),
+    ]
+
+
 class CsaGatherKvArgs(ctypes.Structure):
     """Mirror of ``csa_gather_kv_args_t`` (the arguments of csa_gather_kv, for csa_run_batch)."""
 
@@ -213,7 +245,7 @@ class CsaCall(ctypes.Structure):
 
 
 CSA_CALL_LINEAR, CSA_CALL_ATTN, CSA_CALL_GATHER_KV, CSA_CALL_PEER_SCATTER, CSA_CALL_PEER_SIGNAL, \
-    CSA_CALL_EVENT_RECORD, CSA_CALL_EPOCH_ADVANCE = 1, 2, 3, 4, 5, 6, 7
+    CSA_CALL_EVENT_RECORD, CSA_CALL_EPOCH_ADVANCE, CSA_CALL_GEMM = 1, 2, 3, 4, 5, 6, 7, 8
 
 CSA_ATTN_NO_SPLIT = 1
 CSA_ATTN_B_FIRST = 2
@@ -225,7 +257,7 @@ _lib: Optional[ctypes.CDLL] = None
 # attention launches on the launching stream; both are read by bench.py.
 LAUNCHES = {"csa_attn_fwd": 0, "csa_compact_rows": 0, "csa_validate_mask": 0, "csa_gather_rows": 0,
             "csa_sample_ranges": 0, "csa_gather_kv": 0, "csa_peer_scatter_kv": 0, "csa_peer_signal": 0,
-            "csa_linear": 0, "csa_epoch_advance": 0}
+            "csa_linear": 0, "csa_epoch_advance": 0, "csa_gemm": 0, "csa_sample_positions": 0}
 ATTN_EVENTS: Optional[list] = None   # when a list: (start_event, end_event, n_groups, n_frames, n_q, heads) appended
 
 
@@ -296,6 +328,12 @@ def load() -> ctypes.CDLL:
     lib.csa_ipc_close.argtypes = [c_void_p]
     lib.csa_linear.restype = c_int32
     lib.csa_linear.argtypes = [POINTER(CsaLinearArgs), c_void_p]
+    lib.csa_gemm.restype = c_int32
+    lib.csa_gemm.argtypes = [POINTER(CsaGemmArgs), c_void_p]
+    lib.csa_gemm_supported.restype = c_int32
+    lib.csa_gemm_supported.argtypes = [c_int64, c_int64, c_int64]
+    lib.csa_sample_positions.restype = c_int32
+    lib.csa_sample_positions.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
     lib.csa_run_batch.restype = c_int32
     lib.csa_run_batch.argtypes = [POINTER(CsaCall), c_int32, c_void_p, POINTER(c_int32)]
 
@@ -378,7 +416,8 @@ _BATCH_STREAM: int = 0
 _BATCH_LIKE: Optional[torch.Tensor] = None   # a tensor of the batch's device (device guard at flush)
 _BATCH_NAMES = {CSA_CALL_LINEAR: "csa_linear", CSA_CALL_ATTN: "csa_attn_fwd", CSA_CALL_GATHER_KV: "csa_gather_kv",
                 CSA_CALL_PEER_SCATTER: "csa_peer_scatter_kv", CSA_CALL_PEER_SIGNAL: "csa_peer_signal",
-                CSA_CALL_EVENT_RECORD: "cudaEventRecord", CSA_CALL_EPOCH_ADVANCE: "csa_epoch_advance"}
+                CSA_CALL_EVENT_RECORD: "cudaEventRecord", CSA_CALL_EPOCH_ADVANCE: "csa_epoch_advance",
+                CSA_CALL_GEMM: "csa_gemm"}
 
 
 def begin_batch(like: torch.Tensor) -> None:
@@ -499,6 +538,71 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     lib = load()
     _issue(CSA_CALL_LINEAR, a, lambda st: lib.csa_linear(ctypes.byref(a), st), "csa_linear", _stream_ptr(x), x)
     LAUNCHES["csa_linear"] += 1
+    return out
+
+
+def gemm_supported(m: int, n: int, k: int) -> bool:
+    """Shapes the hand-written GEMM takes (N % 128 == 0, K % 64 == 0); anything else stays with ``linear``."""
+    return bool(load().csa_gemm_supported(m, n, k))
+
+
+def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         alpha: float = 1.0, scatter=None) -> torch.Tensor:
+    """``out[M, N] = alpha * x[M, K] @ w[N, K].T (+ bias)`` with the hand-written sm_100a GEMM (see csa_gemm), same
+    layouts as ``linear``; batchable.  ``scatter = (pos, k_s, v_s, group_rows, dst_group_rows, split_col)`` fuses the
+    gather of the sampled key rows into the epilogue (w = [w_k; w_v]): a row ``r`` with ``pos[r % group_rows] >= 0``
+    is also stored into ``k_s`` / ``v_s`` at row ``(r // group_rows) * dst_group_rows + pos``."""
+    _require_cuda(x, w)
+    ensure_device(x.device)
+    if x.dim() != 2 or w.dim() != 2 or x.stride(1) != 1 or w.stride(1) != 1 or x.shape[1] != w.shape[1] or \
+            w.dtype != x.dtype:
+        raise CsaNativeError("gemm expects 2-D x (M, K) and w (N, K) of one 16-bit dtype, unit column stride")
+    m, k = x.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty((m, n), dtype=x.dtype, device=x.device)
+    elif out.shape != (m, n) or out.stride(1) != 1 or out.dtype != x.dtype:
+        raise CsaNativeError("gemm: out must be (M, N) of x's dtype with unit column stride")
+    a = CsaGemmArgs()
+    a.struct_size = ctypes.sizeof(CsaGemmArgs)
+    a.dtype = dtype_code(x.dtype)
+    a.m, a.n, a.k = m, n, k
+    a.x, a.ldx = x.data_ptr(), x.stride(0)
+    a.w, a.ldw = w.data_ptr(), w.stride(0)
+    if bias is not None:
+        if bias.dtype != x.dtype or bias.numel() != n or not bias.is_contiguous():
+            raise CsaNativeError("gemm: bias must be a contiguous (N,) tensor of x's dtype")
+        a.bias = bias.data_ptr()
+    a.y, a.ldy = out.data_ptr(), out.stride(0)
+    a.alpha = alpha
+    if scatter is not None:
+        pos, k_s, v_s, group_rows, dst_group_rows, split_col = scatter
+        if pos.dtype != torch.int32 or not pos.is_contiguous() or pos.numel() < group_rows or \
+                k_s.dim() != 2 or k_s.stride(1) != 1 or v_s.shape != k_s.shape or v_s.stride(0) != k_s.stride(0) or \
+                k_s.dtype != x.dtype or k_s.shape[1] < split_col or k_s.shape[0] < (m // group_rows) * dst_group_rows:
+            raise CsaNativeError("gemm: bad scatter buffers")
+        a.scatter_pos, a.scatter_k, a.scatter_v = pos.data_ptr(), k_s.data_ptr(), v_s.data_ptr()
+        a.scatter_ld, a.scatter_group_rows = k_s.stride(0), group_rows
+        a.scatter_dst_group_rows, a.split_col = dst_group_rows, split_col
+    lib = load()
+    _issue(CSA_CALL_GEMM, a, lambda st: lib.csa_gemm(ctypes.byref(a), st), "csa_gemm", _stream_ptr(x), x)
+    LAUNCHES["csa_gemm"] += 1
+    return out
+
+
+def sample_positions(s_idx: torch.Tensor, s_count: torch.Tensor, n_cols: int,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """pos [n_cols] int32: index of every column in the ascending list ``s_idx`` (or -1); see csa_sample_positions."""
+    flush_batch()
+    _require_cuda(s_idx, s_count)
+    ensure_device(s_idx.device)
+    if out is None:
+        out = torch.empty((n_cols,), dtype=torch.int32, device=s_idx.device)
+    with _on_device_of(s_idx):
+        rc = load().csa_sample_positions(s_idx.data_ptr(), s_count.data_ptr(), n_cols, out.data_ptr(),
+                                         _stream_ptr(s_idx))
+    _check(rc, "csa_sample_positions")
+    LAUNCHES["csa_sample_positions"] += 1
     return out
 
 

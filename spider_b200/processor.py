@@ -75,6 +75,12 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
     validate_masks = True
     kv_gather = "pre"       # "pre": sampled K/V rows gathered once per layer (csa_gather_kv) and streamed as plain
                             # TMA tiles; "inline": per-frame index lists, TMA gather4 inside the attention kernel
+    native_gemm = True      # the projections run on the hand-written sm_100a GEMM (csa_gemm) when the shape allows
+                            # (N % 128 == 0, K % 64 == 0: every SDXL attn1 layer), else on cuBLASLt (csa_linear)
+    gemm_qo = True          # to_q / to_out[0] on the hand-written GEMM too (False: cuBLASLt for those two, a few us
+                            # faster per layer at F = 4 — profiles/r02_gemm.md — at the price of library launches)
+    fused_gather = True     # consistent write pass: the K|V projection's epilogue stores the sampled rows straight
+                            # into K[S] / V[S] (no csa_gather_kv launch, no second pass over K and V)
     native_projections = True   # to_q / to_k|to_v (one GEMM) / to_out[0] issued by the library
                             # (csa_linear) and the whole call handed over in one batch (csa_run_batch) whenever the
                             # attn module is the plain SDXL attn1 shape (bias-free Linear q/k/v, Linear + Dropout(0)
@@ -192,12 +198,15 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
             native.begin_batch(x)
             try:
                 x2 = x.view(B * N, C)
-                q = native.linear(x2, plan[1])
+                q = self._proj(x2, plan[1])
                 # K and V in one GEMM: columns [0, C) and [C, 2C) — written straight into the bank arena's slot of
-                # this step when the write pass keeps K/V there
-                slot = self._arena_slot(cur_step, B * N, 2 * C, x) if write and self.bank_capacity else None
-                kv = native.linear(x2, plan[2], out=slot)
+                # this step when the write pass keeps K/V there.  The GEMM itself is issued once the branch is known
+                # (_attend_and_project): in the consistent write pass its epilogue also fills K[S] / V[S].
+                kv = self._arena_slot(cur_step, B * N, 2 * C, x) if write and self.bank_capacity else None
+                if kv is None:
+                    kv = torch.empty((B * N, 2 * C), dtype=x.dtype, device=x.device)
                 k, v = kv[:, :C], kv[:, C:]
+                kv_job = (x2, plan[2], kv)
             except Exception:
                 native.abort_batch()
                 raise
@@ -205,12 +214,36 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
             q = attn.to_q(x).view(B * N, C)
             k = attn.to_k(x).view(B * N, C)
             v = attn.to_v(x).view(B * N, C)
+            kv_job = None
         try:
             return self._attend_and_project(attn, h, hidden_states, residual, input_ndim, q, k, v, B, N, C, heads,
-                                            write, cur_step, plan)
+                                            write, cur_step, plan, kv_job)
         except Exception:
             native.abort_batch()
             raise
+
+    def _proj(self, x, w, bias=None, out=None, scatter=None, kv=False):
+        """One projection: the hand-written GEMM when the shape allows, else cuBLASLt (never with a fused gather)."""
+        if self.native_gemm and (kv or self.gemm_qo) and native.gemm_supported(x.shape[0], w.shape[0], x.shape[1]):
+            return native.gemm(x, w, bias, out=out, scatter=scatter)
+        if scatter is not None:
+            raise native.CsaNativeError("fused gather needs the hand-written GEMM (shape not supported)")
+        return native.linear(x, w, bias, out=out)
+
+    _KS_BUFFERS: dict = {}
+
+    @classmethod
+    def _ks_buffers(cls, device, rows: int, C: int, dtype):
+        """The (K[S], V[S]) buffer pair of one layer shape on one device: shared by all layers of that shape (they run
+        one after the other on the stream), zero once — rows past the current sample count keep finite values of an
+        earlier step and are masked by the kernel's key counts."""
+        key = (device.index, rows, C, dtype)
+        hit = cls._KS_BUFFERS.get(key)
+        if hit is None:
+            native.flush_batch()   # torch.zeros launches a fill: nothing deferred may be overtaken
+            hit = cls._KS_BUFFERS[key] = (torch.zeros((rows, C), dtype=dtype, device=device),
+                                          torch.zeros((rows, C), dtype=dtype, device=device))
+        return hit
 
     def _arena_slot(self, step, rows: int, cols: int, like: torch.Tensor):
         """K|V buffer ``(rows, 2C)`` of ``step`` inside this layer's preallocated arena (``bank_capacity`` steps), or
@@ -276,7 +309,7 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
         return hit if ok else None
 
     def _attend_and_project(self, attn, h, hidden_states, residual, input_ndim, q, k, v, B, N, C, heads, write,
-                            cur_step, plan):
+                            cur_step, plan, kv_job=None):
         Fl = self.id_length
         use_native = plan is not None
         entry: Optional[BankEntry] = None
@@ -301,8 +334,15 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                                  + ("" if self.batched_read else " (set batched_read=True for 2*R frames)"))
 
         o = torch.empty_like(q)
+
+        def project_kv(scatter=None):
+            # the K|V projection of the current input, deferred until the branch is known (native path only)
+            if kv_job is not None:
+                self._proj(kv_job[0], kv_job[1], out=kv_job[2], scatter=scatter, kv=True)
+
         branch = "early"
         if cur_step < 5:                                        # :94-96
+            project_kv()
             if write:
                 self._attn_standard(q, k, v, o, B, N, heads)
             else:
@@ -319,16 +359,30 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                         raise ValueError(f"consistent write pass expects batch 2*id_length={2 * Fl}"
                                          f"{'' if self.dist is None else f' sharded to {want_b} per rank'}, got {B} "
                                          "(the reference fails with a mask shape error here)")
-                    self._attn_write(q, k, v, o, N, heads, cm)
+                    fused = None
+                    if (kv_job is not None and self.fused_gather and self.native_gemm and self.dist is None
+                            and self.kv_gather == "pre" and cm.shared_sample
+                            and native.gemm_supported(B * N, 2 * C, C)):
+                        # the K|V GEMM's epilogue stores the sampled rows into K[S] / V[S] (no gather launch)
+                        cap = Fl * N + native.CSA_TILE
+                        pos = cm.sample_positions(q.device)
+                        k_s, v_s = self._ks_buffers(q.device, 2 * cap, C, q.dtype)
+                        fused = (k_s, v_s, cap)
+                        project_kv(scatter=(pos, k_s, v_s, Fl * N, cap, C))
+                    else:
+                        project_kv()
+                    self._attn_write(q, k, v, o, N, heads, cm, fused)
                 else:
+                    project_kv()
                     self._attn_read(attn, entry, q, k, v, o, N, heads, cm=cm, plan=plan)
             else:
                 branch = "standard"
+                project_kv()
                 self._attn_standard(q, k, v, o, B, N, heads)    # :118 — bank ignored even when reading
         self._last_branch = branch
 
         if use_native:
-            out = native.linear(o, plan[3], plan[4]).view(B, N, C)   # :185 / :256
+            out = self._proj(o, plan[3], plan[4]).view(B, N, C)      # :185 / :256
             native.flush_batch()                                # everything collected since the projections: ONE call
         else:
             out = o.view(B, N, C)
@@ -363,7 +417,7 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
         native.attn_fwd(q, o, heads=heads, n_groups=1, n_frames=B, n_q=N,
                         k_b=k, v_b=v, b_group_rows=B * N, cb=(0, N, N))
 
-    def _attn_write(self, q, k, v, o, N, heads, cm):
+    def _attn_write(self, q, k, v, o, N, heads, cm, fused=None):
         """__call1__ in write mode (:129-196 with mask[:F*N,:F*N]): frame f attends its own block plus the sampled
         rows of all identity frames of the same CFG half."""
         Fl = self.id_length
@@ -373,7 +427,10 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
             # mask row f = S u block_f: gather K[S], V[S] once (HBM-bound), then frame f attends the two runs of that
             # buffer that lie outside its own block + its own block in place
             s_idx, s_count, ranges = cm.sample_list(q.device)
-            k_s, v_s, cap = native.gather_kv(k, v, Fl * N, 2, s_idx, s_count, Fl * N)
+            if fused is not None:
+                k_s, v_s, cap = fused         # filled by the K|V projection's epilogue
+            else:
+                k_s, v_s, cap = native.gather_kv(k, v, Fl * N, 2, s_idx, s_count, Fl * N)
             native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=Fl, n_q=N,
                             k_a=k_s, v_a=v_s, a_group_rows=cap, ranges=ranges, range_base=0, range_step=1,
                             k_b=k, v_b=v, b_group_rows=Fl * N, cb=(0, N, N))
@@ -399,7 +456,7 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
             hs = hs.to(device=dev, dtype=q.dtype).reshape(Fl * N, C)
             native.gather_rows(hs, s_idx, Fl * N, count=s_count, out=g[half * cap:half * cap + Fl * N])
         if plan is not None:
-            kv = native.linear(g, plan[2])
+            kv = self._proj(g, plan[2], kv=True)
             return kv[:, :C], kv[:, C:], cap, ranges
         return attn.to_k(g), attn.to_v(g), cap, ranges
 

@@ -1,0 +1,97 @@
+"""The hand-written sm_100a projection GEMM (csrc/gemm_sm100.cu, `-m gpu` on a B200) against a plain PyTorch fp32
+reference of the same op: y = alpha * x w^T + bias with nn.Linear layouts, ragged M, strided operands, both 16-bit
+types, every SDXL attn1 shape; and the fused gather of the sampled K/V rows against csa_gather_kv (bit-exact: the
+same values, stored twice)."""
+import pytest
+import torch
+
+from spider_b200 import masks as csa_masks
+from spider_b200 import native
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ref(x, w, bias, alpha):
+    y = alpha * (x.float() @ w.float().t())
+    if bias is not None:
+        y = y + bias.float()
+    return y
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("m,n,k,bias", [(8192, 1280, 1280, False), (8192, 2560, 1280, False), (4096, 1280, 1280, True),
+                                        (32768, 640, 640, True), (32768, 1280, 640, False), (1000, 640, 640, True),
+                                        (130, 128, 64, False), (1, 256, 128, True), (4608, 2560, 1280, False)])
+def test_gemm_matches_torch_fp32(dtype, m, n, k, bias):
+    assert native.gemm_supported(m, n, k)
+    g = torch.Generator(device=DEV).manual_seed(m + n + k)
+    x = torch.randn((m, k), device=DEV, generator=g).to(dtype)
+    w = (torch.randn((n, k), device=DEV, generator=g) * k ** -0.5).to(dtype)
+    b = torch.randn((n,), device=DEV, generator=g).to(dtype) if bias else None
+    y = native.gemm(x, w, b)
+    torch.cuda.synchronize()
+    want = _ref(x, w, b, 1.0)
+    err = (y.float() - want).abs().max().item()
+    tol = 2e-2 if dtype == torch.bfloat16 else 4e-3     # output rounding of a 16-bit y with |y| up to ~5
+    assert err <= tol, f"max-abs {err:.3e}"
+    # against the cuBLASLt path: same inputs, same fp32 accumulation, same 16-bit rounding of the result
+    y2 = native.linear(x, w, b)
+    torch.cuda.synchronize()
+    assert (y.float() - y2.float()).abs().max().item() <= tol
+
+
+def test_gemm_alpha_strides_and_out():
+    dtype = torch.bfloat16
+    g = torch.Generator(device=DEV).manual_seed(1)
+    big = torch.randn((700, 1280 + 64), device=DEV, generator=g).to(dtype)
+    x = big[:, 64:]                                        # row stride 1344, 128-byte aligned start
+    w = (torch.randn((1280, 1280), device=DEV, generator=g) * 0.03).to(dtype)
+    out = torch.zeros((700, 2560), device=DEV, dtype=dtype)
+    y = native.gemm(x, w, out=out[:, 1280:], alpha=0.125)
+    torch.cuda.synchronize()
+    assert y.data_ptr() == out[:, 1280:].data_ptr() and float(out[:, :1280].abs().max()) == 0.0
+    want = _ref(x, w, None, 0.125)
+    assert (y.float() - want).abs().max().item() <= 5e-3
+
+
+def test_gemm_rejects_bad_arguments():
+    x = torch.zeros((128, 64), device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros((128, 64), device=DEV, dtype=torch.bfloat16)
+    assert not native.gemm_supported(128, 100, 64) and not native.gemm_supported(128, 128, 48)
+    with pytest.raises(native.CsaNativeError):
+        native.gemm(x, torch.zeros((100, 64), device=DEV, dtype=torch.bfloat16))
+    with pytest.raises(native.CsaNativeError):
+        native.gemm(x, w.to(torch.float16))
+    native.abort_batch()
+
+
+@pytest.mark.parametrize("Fl,N,C", [(4, 1024, 1280), (4, 4096, 640), (3, 576, 1280)])
+def test_fused_gather_equals_gather_kv(Fl, N, C):
+    """K|V projection with the fused gather: K[S] / V[S] filled by the epilogue are bit-identical to csa_gather_kv run
+    on the projection's own output, for both CFG halves; rows that are not sampled are not touched."""
+    dtype = torch.bfloat16
+    T = Fl + 1
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn((2 * Fl * N, C), device=DEV, generator=g).to(dtype)
+    w_kv = (torch.randn((2 * C, C), device=DEV, generator=g) * C ** -0.5).to(dtype)
+    sample = torch.rand((T * N,), device=DEV, generator=g) < 0.5
+    cm = csa_masks.CompactMask(T, Fl, N, sample=sample)
+    s_idx, s_count, _ = cm.sample_list(DEV)
+    pos = cm.sample_positions(DEV)
+    cnt = int(s_count.item())
+    # the inverse list: pos[s_idx[i]] == i, -1 elsewhere
+    want_pos = torch.full((Fl * N,), -1, dtype=torch.int32, device=DEV)
+    want_pos[s_idx[:cnt].long()] = torch.arange(cnt, dtype=torch.int32, device=DEV)
+    assert torch.equal(pos, want_pos)
+    cap = Fl * N + native.CSA_TILE
+    k_s = torch.full((2 * cap, C), 7.0, device=DEV, dtype=dtype)
+    v_s = torch.full((2 * cap, C), 7.0, device=DEV, dtype=dtype)
+    kv = native.gemm(x, w_kv, scatter=(pos, k_s, v_s, Fl * N, cap, C))
+    k_ref, v_ref, cap2 = native.gather_kv(kv[:, :C], kv[:, C:], Fl * N, 2, s_idx, s_count, Fl * N)
+    torch.cuda.synchronize()
+    assert cap2 == cap
+    for grp in range(2):
+        assert torch.equal(k_s[grp * cap:grp * cap + cnt], k_ref[grp * cap:grp * cap + cnt])
+        assert torch.equal(v_s[grp * cap:grp * cap + cnt], v_ref[grp * cap:grp * cap + cnt])
+        assert float((k_s[grp * cap + cnt:(grp + 1) * cap].float() - 7.0).abs().max()) == 0.0   # untouched

@@ -13,7 +13,7 @@ for v in "$@"; do
   shift
   nvcc $ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -Xptxas -v \
     -c attn_sm100.cu -o build/attn_$name.o 2>&1 | grep -i "spill\|error" || true
-  nvcc $ARCH -shared -o ../variants/libcsa_$name.so build/abi.o build/compact.o build/peer.o build/linear.o \
+  nvcc $ARCH -shared -o ../variants/libcsa_$name.so build/abi.o build/compact.o build/peer.o build/linear.o build/gemm_sm100.o \
     build/attn_$name.o -lcudart -lcublasLt -Xlinker -rpath=/usr/local/cuda/lib64
   echo built $name
 done

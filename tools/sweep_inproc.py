@@ -62,7 +62,8 @@ def main():
                 continue
             for sa in a.sas:
                 args = argparse.Namespace(res=res, sa=sa, placement=a.placement, module_projections=False,
-                                          exchange=a.exchange, share_weights=True, graph=a.graph, frames=F)
+                                          exchange=a.exchange, share_weights=True, graph=a.graph, frames=F,
+                                          projections="own")
                 try:
                     wl = bench.Workload(args, F, dev, dtype, world, rank, shard_cache)
                     with torch.no_grad():
