@@ -38,10 +38,11 @@ def launches(path: str):
     # the last warm step = everything after the (n_steps-1)-th mask re-sampling; simpler: take the last 1/4 of the
     # attention launches' span.  bench.py ran 3 warm-up steps + 1 timed step => 4 identical steps.
     attn_ids = [i for i, (_, k, *_r) in enumerate(rows) if "csa_attn_kernel" in k]
-    per_step = len(attn_ids) // 4 if len(attn_ids) >= 4 else len(attn_ids)
+    # one step = the last ATTN_PER_STEP attention launches (36 for the reference placement, 70 for --placement all)
+    per_step = min(int(os.environ.get("ATTN_PER_STEP", "36")), len(attn_ids))
     first = attn_ids[-per_step] if per_step else 0
-    # include the projections that precede the first attention launch of the step (3 GEMMs)
-    first = max(0, first - 3)
+    # include the projections that precede the first attention launch of the step (q and k|v GEMMs)
+    first = max(0, first - 2)
     step = rows[first:]
     agg = OrderedDict()
     for _, k, grid, block, us in step:
