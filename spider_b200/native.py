@@ -11,6 +11,7 @@ from __future__ import annotations
 import contextlib
 import ctypes
 import os
+import threading
 from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint8, c_uint32, c_void_p
 from typing import Optional
 
@@ -411,9 +412,19 @@ def dtype_code(dt: torch.dtype) -> int:
 # argument blocks; flush_batch() hands the whole sequence to csa_run_batch — one transition into the library per
 # processor call.  Nothing else may be enqueued on the stream in between (torch kernels would overtake the batch):
 # code that has to do so calls flush_batch() first.
-_BATCH: Optional[list] = None
-_BATCH_STREAM: int = 0
-_BATCH_LIKE: Optional[torch.Tensor] = None   # a tensor of the batch's device (device guard at flush)
+class _BatchState(threading.local):
+    """Per-thread deferred-launch state: two threads driving processors (a multi-pipeline server) never interleave
+    their batches.  ``calls`` holds ``(kind, args, keep)`` — ``keep`` references every tensor whose pointer the
+    argument block carries, so that nothing a deferred launch reads or writes can be freed and re-used before the
+    batch is flushed."""
+
+    def __init__(self):
+        self.calls: Optional[list] = None
+        self.stream: int = 0
+        self.like: Optional[torch.Tensor] = None   # a tensor of the batch's device (device guard at flush)
+
+
+_TLS = _BatchState()
 _BATCH_NAMES = {CSA_CALL_LINEAR: "csa_linear", CSA_CALL_ATTN: "csa_attn_fwd", CSA_CALL_GATHER_KV: "csa_gather_kv",
                 CSA_CALL_PEER_SCATTER: "csa_peer_scatter_kv", CSA_CALL_PEER_SIGNAL: "csa_peer_signal",
                 CSA_CALL_EVENT_RECORD: "cudaEventRecord", CSA_CALL_EPOCH_ADVANCE: "csa_epoch_advance",
@@ -421,28 +432,26 @@ _BATCH_NAMES = {CSA_CALL_LINEAR: "csa_linear", CSA_CALL_ATTN: "csa_attn_fwd", CS
 
 
 def begin_batch(like: torch.Tensor) -> None:
-    global _BATCH, _BATCH_STREAM, _BATCH_LIKE
-    if _BATCH is not None:
+    if _TLS.calls is not None:
         flush_batch()
-    _BATCH = []
-    _BATCH_STREAM = _stream_ptr(like)
-    _BATCH_LIKE = like
+    _TLS.calls = []
+    _TLS.stream = _stream_ptr(like)
+    _TLS.like = like
 
 
 def flush_batch() -> None:
     """Issue what has been collected (no-op when no batch is open) and close the batch."""
-    global _BATCH
-    calls, _BATCH = _BATCH, None
+    calls, _TLS.calls = _TLS.calls, None
     if not calls:
         return
     n = len(calls)
     arr = (CsaCall * n)()
-    for i, (kind, a) in enumerate(calls):
+    for i, (kind, a, _keep) in enumerate(calls):
         arr[i].kind = kind
         arr[i].args = a if isinstance(a, int) else ctypes.addressof(a)
     failed = c_int32(-1)
-    with (_on_device_of(_BATCH_LIKE) if _BATCH_LIKE is not None else _NULL_CTX):
-        rc = load().csa_run_batch(arr, n, _BATCH_STREAM, ctypes.byref(failed))
+    with (_on_device_of(_TLS.like) if _TLS.like is not None else _NULL_CTX):
+        rc = load().csa_run_batch(arr, n, _TLS.stream, ctypes.byref(failed))
     if rc != 0:
         what = _BATCH_NAMES.get(calls[failed.value][0], "?") if 0 <= failed.value < n else "csa_run_batch"
         _check(rc, f"{what} (entry {failed.value} of a batch of {n})")
@@ -450,14 +459,14 @@ def flush_batch() -> None:
 
 def abort_batch() -> None:
     """Drop an open batch without issuing it (error paths)."""
-    global _BATCH
-    _BATCH = None
+    _TLS.calls = None
 
 
-def _issue(kind: int, a, direct, what: str, stream: int, like: Optional[torch.Tensor] = None) -> None:
-    """Launch now (with ``like``'s device current), or defer into the open batch (same stream only)."""
-    if _BATCH is not None and stream == _BATCH_STREAM:
-        _BATCH.append((kind, a))
+def _issue(kind: int, a, direct, what: str, stream: int, like: Optional[torch.Tensor] = None, keep=()) -> None:
+    """Launch now (with ``like``'s device current), or defer into the open batch (same stream only); ``keep`` = the
+    tensors the argument block points into."""
+    if _TLS.calls is not None and stream == _TLS.stream:
+        _TLS.calls.append((kind, a, keep))
     else:
         with (_on_device_of(like) if like is not None else _NULL_CTX):
             _check(direct(stream), what)
@@ -479,8 +488,8 @@ def record_event(ev: "torch.cuda.Event", stream: int) -> None:
     """Record a timing event through the library (CSA_CALL_EVENT_RECORD): on a stream that is being captured into a
     CUDA graph this makes an event-record NODE whose time can be read after a replay, which torch's own
     ``Event.record()`` (a plainly captured event) does not allow."""
-    if _BATCH is not None and stream == _BATCH_STREAM:
-        _BATCH.append((CSA_CALL_EVENT_RECORD, ev.cuda_event))
+    if _TLS.calls is not None and stream == _TLS.stream:
+        _TLS.calls.append((CSA_CALL_EVENT_RECORD, ev.cuda_event, (ev,)))
         return
     arr = (CsaCall * 1)()
     arr[0].kind = CSA_CALL_EVENT_RECORD
@@ -499,11 +508,14 @@ def prepare_event_pool(n: int) -> None:
 _LINEAR_WS: dict = {}
 
 
-def _linear_workspace(device: torch.device) -> torch.Tensor:
+def _linear_workspace(device: torch.device, stream: int) -> torch.Tensor:
+    """cuBLASLt scratch, one per (device, stream): launches on one stream are ordered and may share it, two streams
+    (two pipelines of one server) must not."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    ws = _LINEAR_WS.get(idx)
+    ws = _LINEAR_WS.get((idx, stream))
     if ws is None:
-        ws = _LINEAR_WS[idx] = torch.empty(32 << 20, dtype=torch.uint8, device=device)
+        flush_batch()
+        ws = _LINEAR_WS[(idx, stream)] = torch.empty(32 << 20, dtype=torch.uint8, device=device)
     return ws
 
 
@@ -533,10 +545,11 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
             raise CsaNativeError("linear: bias must be a contiguous (N,) tensor of x's dtype")
         a.bias = bias.data_ptr()
     a.y, a.ldy = out.data_ptr(), out.stride(0)
-    ws = _linear_workspace(x.device)
+    ws = _linear_workspace(x.device, _stream_ptr(x))
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     lib = load()
-    _issue(CSA_CALL_LINEAR, a, lambda st: lib.csa_linear(ctypes.byref(a), st), "csa_linear", _stream_ptr(x), x)
+    _issue(CSA_CALL_LINEAR, a, lambda st: lib.csa_linear(ctypes.byref(a), st), "csa_linear", _stream_ptr(x), x,
+           keep=(x, w, bias, out, ws))
     LAUNCHES["csa_linear"] += 1
     return out
 
@@ -585,7 +598,8 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         a.scatter_ld, a.scatter_group_rows = k_s.stride(0), group_rows
         a.scatter_dst_group_rows, a.split_col = dst_group_rows, split_col
     lib = load()
-    _issue(CSA_CALL_GEMM, a, lambda st: lib.csa_gemm(ctypes.byref(a), st), "csa_gemm", _stream_ptr(x), x)
+    _issue(CSA_CALL_GEMM, a, lambda st: lib.csa_gemm(ctypes.byref(a), st), "csa_gemm", _stream_ptr(x), x,
+           keep=(x, w, bias, out, scatter))
     LAUNCHES["csa_gemm"] += 1
     return out
 
@@ -715,7 +729,7 @@ def gather_kv(k: torch.Tensor, v: torch.Tensor, group_rows: int, n_groups: int, 
     _issue(CSA_CALL_GATHER_KV, a,
            lambda st: lib.csa_gather_kv(a.k, a.v, a.ld_bytes, a.group_rows, a.n_groups, a.s_idx, a.s_count, a.max_rows,
                                         a.k_out, a.v_out, a.out_ld_bytes, a.out_group_rows, a.row_bytes, st),
-           "csa_gather_kv", _stream_ptr(k), k)
+           "csa_gather_kv", _stream_ptr(k), k, keep=(k, v, s_idx, s_count, k_s, v_s))
     LAUNCHES["csa_gather_kv"] += 1
     return k_s, v_s, out_group_rows
 
@@ -814,16 +828,17 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
             raise CsaNativeError("ranges must be a contiguous int32 tensor of shape (lists, 4)")
         a.ranges, a.range_base, a.range_step = ranges.data_ptr(), range_base, range_step
     lib = load()
+    keep = (q, o, k_a, v_a, k_b, v_b, idx, counts, ranges, ready, epoch_base)
     direct = lambda st: lib.csa_attn_fwd(ctypes.byref(a), st)   # noqa: E731
     if ATTN_EVENTS is not None:
         # kernel time of the attention launches on the launching stream (bench.py's roofline line)
         e0, e1 = _pooled_event(), _pooled_event()
         record_event(e0, stream)
-        _issue(CSA_CALL_ATTN, a, direct, "csa_attn_fwd", stream, q)
+        _issue(CSA_CALL_ATTN, a, direct, "csa_attn_fwd", stream, q, keep=keep)
         record_event(e1, stream)
         ATTN_EVENTS.append((e0, e1, n_groups, n_frames, n_q, heads))
     else:
-        _issue(CSA_CALL_ATTN, a, direct, "csa_attn_fwd", stream, q)
+        _issue(CSA_CALL_ATTN, a, direct, "csa_attn_fwd", stream, q, keep=keep)
     LAUNCHES["csa_attn_fwd"] += 1
     return o
 
@@ -870,7 +885,7 @@ def peer_scatter_kv(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, count: 
         a.ranges, a.frames_per_peer, a.idx_adjust = ranges.data_ptr(), frames_per_peer, idx_adjust
     lib = load()
     _issue(CSA_CALL_PEER_SCATTER, a, lambda st: lib.csa_peer_scatter_kv(ctypes.byref(a), st), "csa_peer_scatter_kv",
-           _stream_ptr(k), k)
+           _stream_ptr(k), k, keep=(k, v, idx, k_dst, v_dst, ready, done, counter, ranges, epoch_base))
     LAUNCHES["csa_peer_scatter_kv"] += 1
 
 

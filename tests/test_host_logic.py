@@ -314,7 +314,8 @@ def test_batch_defers_in_order_and_flushes_before_immediate_calls(monkeypatch):
     monkeypatch.setattr(native, "_stream_ptr", lambda t: 7)
     monkeypatch.setattr(native, "_require_cuda", lambda *a: None)
     monkeypatch.setattr(native, "ensure_device", lambda d: None)
-    monkeypatch.setattr(native, "_linear_workspace", lambda d: torch.zeros(64, dtype=torch.uint8))
+    monkeypatch.setattr(native, "_linear_workspace", lambda d, st: torch.zeros(64, dtype=torch.uint8))
+    monkeypatch.setattr(native, "_on_device_of", lambda t: native._NULL_CTX)
     x = torch.zeros((8, 16), dtype=torch.bfloat16)
     w = torch.zeros((32, 16), dtype=torch.bfloat16)
     # no batch open: immediate
