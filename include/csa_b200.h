@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define CSA_ABI_VERSION 7
+#define CSA_ABI_VERSION 8
 
 #define CSA_E_BADARG (-1)   /* null pointer, non-positive size, misaligned pointer/stride */
 #define CSA_E_SHAPE (-2)    /* unsupported geometry (head_dim != 64, row stride not 16-byte aligned, ...) */
@@ -334,7 +334,8 @@ int csa_linear(const csa_linear_args_t* args, void* stream);
 /*
  * The same projections as a HAND-WRITTEN sm_100a GEMM (csrc/gemm_sm100.cu: TMA-fed 5-stage ring, tcgen05.mma M128 N128
  * K16 with two TMEM accumulators, epilogue in registers):  y = alpha * x w^T (+ bias), layouts as csa_linear.  Shapes of
- * the path only: N % 128 == 0 and K % 64 == 0 (csa_gemm_supported); anything else stays with csa_linear.
+ * the path only: N % 128 == 0 and K % 64 == 0 (csa_gemm_supported); anything else stays with csa_linear.  With a
+ * stacked weight [w_q; w_k; w_v] (n = 3C) ONE launch projects q, K and V of a layer: y = q, y2 = K|V (y_split = C).
  *
  * Fused K/V gather (optional, the write pass of the consistent branch, Comic_Generation.py:164-165 feeding :175-177):
  * when x holds `m / scatter_group_rows` groups (CFG halves) of key rows and w = [w_k; w_v] (n = 2C, split_col = C),
@@ -364,6 +365,13 @@ typedef struct csa_gemm_args {
   int32_t scatter_group_rows;
   int32_t scatter_dst_group_rows;
   int32_t split_col;
+  int32_t scatter_col0; /* columns below it are not gathered: w = [w_q; w_k; w_v], scatter_col0 = C, split_col = 2C */
+  /* Optional second output matrix: columns [y_split, n) of the product go to y2[:, col - y_split] (leading dimension
+   * ldy2) instead of y — q and K|V of one stacked-weight GEMM land in two buffers (the id_bank keeps only K|V).
+   * NULL = everything goes to y.  y_split: multiple of 32. */
+  void* y2;
+  int64_t ldy2;
+  int32_t y_split;
   int32_t _pad1;
 } csa_gemm_args_t;
 

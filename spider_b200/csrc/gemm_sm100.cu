@@ -54,6 +54,9 @@ struct GemmParams {
   CUtensorMap tm_x, tm_w;
   void* y;
   int64_t ldy;
+  void* y2;           // optional second output: columns >= y_split go to y2[:, col - y_split]
+  int64_t ldy2;
+  int32_t y_split;    // multiple of 32; == n when there is no second output
   const void* bias;
   float alpha;
   int32_t m, n, k;
@@ -64,6 +67,7 @@ struct GemmParams {
   void* scatter_v;              // V[S]: same rows, columns [split_col, n) shifted down by split_col
   int64_t scatter_ld;
   int32_t scatter_group_rows, scatter_dst_group_rows, split_col;
+  int32_t scatter_col0;  // columns below it are not gathered (the q part of a stacked q|k|v weight)
   uint32_t* dbg;
 };
 
@@ -171,7 +175,6 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
       mbar_wait(GSB(acc_full) + 8u * buf, fph[buf], 0x530 + buf, p.dbg);
       fph[buf] ^= 1;
       tc_fence_after();
-      uint16_t* yrow = reinterpret_cast<uint16_t*>(p.y) + static_cast<int64_t>(row) * p.ldy + n0;
       // fused gather: where this row goes in K[S] / V[S] (or nowhere)
       int pos = -1, g = 0;
       if (p.scatter_pos != nullptr && row_ok) {
@@ -180,12 +183,14 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
       }
 #pragma unroll 1
       for (int c = 0; c < kBN / 32; ++c) {
+        const int col = n0 + c * 32;
+        if (col >= p.n) break;                           // ragged last n tile (N % kBN != 0): nothing beyond N
         uint32_t acc[32];
         tmem_ld32(tmem + lane_base + buf * kBN + c * 32, acc);
         tc_wait_ld();
         float bv[32];
         if (p.bias != nullptr) {
-          const uint4* bp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias) + n0 + c * 32);
+          const uint4* bp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias) + col);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint4 w4 = __ldg(bp + i);
@@ -219,15 +224,18 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
           out[i] = make_uint4(w[0], w[1], w[2], w[3]);
         }
         if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(yrow + c * 32);
+          // a 32-column chunk never straddles y_split / scatter_col0 / split_col (all multiples of 32)
+          uint4* dst = reinterpret_cast<uint4*>(
+              col < p.y_split ? reinterpret_cast<uint16_t*>(p.y) + static_cast<int64_t>(row) * p.ldy + col
+                              : reinterpret_cast<uint16_t*>(p.y2) + static_cast<int64_t>(row) * p.ldy2 + (col - p.y_split));
 #pragma unroll
           for (int i = 0; i < 4; ++i) dst[i] = out[i];
-          if (pos >= 0) {
-            const int col = n0 + c * 32;                 // a 32-column chunk never straddles split_col (% 128 == 0)
+          if (pos >= 0 && col >= p.scatter_col0) {
             const bool is_v = col >= p.split_col;
             uint4* sd = reinterpret_cast<uint4*>(
                 reinterpret_cast<uint16_t*>(is_v ? p.scatter_v : p.scatter_k) +
-                (static_cast<int64_t>(g) * p.scatter_dst_group_rows + pos) * p.scatter_ld + (col - (is_v ? p.split_col : 0)));
+                (static_cast<int64_t>(g) * p.scatter_dst_group_rows + pos) * p.scatter_ld +
+                (col - (is_v ? p.split_col : p.scatter_col0)));
 #pragma unroll
             for (int i = 0; i < 4; ++i) sd[i] = out[i];
           }
@@ -292,7 +300,7 @@ static int gemm_launch(const csa_gemm_args_t* a, GemmParams& p, int dev, int sms
   if ((rc = gemm_encode(&p.tm_x, a->dtype, a->x, a->m, a->k, a->ldx, kGM))) return rc;
   if ((rc = gemm_encode(&p.tm_w, a->dtype, a->w, a->n, a->k, a->ldw, kBN / kCl))) return rc;
   p.pairs_m = static_cast<int32_t>((a->m + kCl * kGM - 1) / (kCl * kGM));
-  p.tiles_n = static_cast<int32_t>(a->n / kBN);
+  p.tiles_n = static_cast<int32_t>((a->n + kBN - 1) / kBN);   // a ragged last tile reads zero rows of w (TMA OOB fill)
   const int n_items = p.pairs_m * p.tiles_n;
   const size_t smem = sizeof(GemmSmem<kBN>) + 1024;
   auto kern = a->dtype == CSA_DTYPE_BF16 ? csa_gemm_kernel<true, kBN, kCl> : csa_gemm_kernel<false, kBN, kCl>;
@@ -343,7 +351,7 @@ extern "C" int csa_gemm(const csa_gemm_args_t* a, void* stream) {
   if (!csa_gemm_supported(a->m, a->n, a->k))
     return set_error(CSA_E_SHAPE, "csa_gemm: needs N %% 128 == 0 and K %% 64 == 0, got M=%lld N=%lld K=%lld",
                      (long long)a->m, (long long)a->n, (long long)a->k);
-  if (a->ldx < a->k || a->ldw < a->k || a->ldy < a->n || ((a->ldx | a->ldw | a->ldy) & 7))
+  if (a->ldx < a->k || a->ldw < a->k || (a->y2 == nullptr && a->ldy < a->n) || ((a->ldx | a->ldw | a->ldy) & 7))
     return set_error(CSA_E_BADARG, "csa_gemm: leading dimensions must cover the rows and be multiples of 8 elements");
   if (!a->x || !a->w || !a->y) return set_error(CSA_E_BADARG, "csa_gemm: null pointer");
   if ((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->w) | reinterpret_cast<uintptr_t>(a->y) |
@@ -353,6 +361,16 @@ extern "C" int csa_gemm(const csa_gemm_args_t* a, void* stream) {
   memset(&p, 0, sizeof(p));
   p.y = a->y;
   p.ldy = a->ldy;
+  p.y2 = a->y2;
+  p.ldy2 = a->ldy2;
+  p.y_split = static_cast<int32_t>(a->n);
+  if (a->y2 != nullptr) {
+    if (a->y_split <= 0 || a->y_split >= a->n || (a->y_split % 32) || a->ldy < a->y_split ||
+        a->ldy2 < a->n - a->y_split || (a->ldy2 & 7) || (reinterpret_cast<uintptr_t>(a->y2) & 15))
+      return set_error(CSA_E_BADARG, "csa_gemm: bad second output (y_split must be a multiple of 32 inside (0, N), "
+                                     "leading dimensions must cover their column ranges)");
+    p.y_split = a->y_split;
+  }
   p.bias = a->bias;
   p.alpha = a->alpha;
   p.m = static_cast<int32_t>(a->m);
@@ -360,11 +378,12 @@ extern "C" int csa_gemm(const csa_gemm_args_t* a, void* stream) {
   p.k = static_cast<int32_t>(a->k);
   if (a->scatter_pos != nullptr) {
     if (!a->scatter_k || !a->scatter_v || a->scatter_group_rows <= 0 || a->scatter_dst_group_rows <= 0 ||
-        a->split_col <= 0 || (a->split_col % 128) || a->split_col > a->n || (a->scatter_ld & 7) ||
+        a->split_col <= 0 || (a->split_col % 32) || a->split_col > a->n || (a->scatter_ld & 7) ||
+        a->scatter_col0 < 0 || (a->scatter_col0 % 32) || a->scatter_col0 > a->split_col ||
         ((reinterpret_cast<uintptr_t>(a->scatter_k) | reinterpret_cast<uintptr_t>(a->scatter_v)) & 15) ||
         (a->m % a->scatter_group_rows))
-      return set_error(CSA_E_BADARG, "csa_gemm: bad scatter arguments (split_col must be a multiple of 128, M a "
-                                     "multiple of scatter_group_rows, buffers 16-byte aligned)");
+      return set_error(CSA_E_BADARG, "csa_gemm: bad scatter arguments (scatter_col0 <= split_col, both multiples of 32, "
+                                     "M a multiple of scatter_group_rows, buffers 16-byte aligned)");
     p.scatter_pos = a->scatter_pos;
     p.scatter_k = a->scatter_k;
     p.scatter_v = a->scatter_v;
@@ -372,6 +391,7 @@ extern "C" int csa_gemm(const csa_gemm_args_t* a, void* stream) {
     p.scatter_group_rows = a->scatter_group_rows;
     p.scatter_dst_group_rows = a->scatter_dst_group_rows;
     p.split_col = a->split_col;
+    p.scatter_col0 = a->scatter_col0;
   }
   p.dbg = debug_record_devptr();
   int dev = 0;
@@ -382,7 +402,10 @@ extern "C" int csa_gemm(const csa_gemm_args_t* a, void* stream) {
   // 128 x 256 tiles halve the operand traffic per FLOP; 128 x 128 when N is not a multiple of 256 (N = 640) or when
   // the wider tile would leave most of the chip without work
   const int64_t blocks_m = (a->m + kGM - 1) / kGM;
-  const bool wide = (a->n % 256) == 0 && blocks_m * (a->n / 256) >= sms / 2;
+  // wide tiles also for N % 256 == 128 (the last n tile is half empty) as long as that wastes < 1/8 of the MMAs
+  // (N = 1920: yes; N = 640: no — measured 45.5 us wide vs 42.0 us narrow)
+  const int64_t tiles_wide = (a->n + 255) / 256;
+  const bool wide = tiles_wide * 256 * 8 <= a->n * 9 && blocks_m * tiles_wide >= sms / 2;
   // CSA_GEMM_CLUSTER=4: four CTAs stacked along M share one w tile instead of two (tuning knob; measured no faster on
   // any shape of the path — 132 instead of 148 SMs can hold clusters of four — profiles/r02_gemm.md)
   static const int cl_env = []() {

@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CSA_B200_LIB: developer knob to load an experimental build of the same ABI (kernel tuning sweeps); default in-tree
 LIB_PATH = os.environ.get("CSA_B200_LIB") or os.path.join(_HERE, "libcsa_b200.so")
 
-CSA_ABI_VERSION = 7
+CSA_ABI_VERSION = 8
 CSA_DTYPE_F16 = 0
 CSA_DTYPE_BF16 = 1
 CSA_TILE = 128
@@ -195,6 +195,10 @@ class CsaGemmArgs(ctypes.Structure):
         ("scatter_group_rows", c_int32),
         ("scatter_dst_group_rows", c_int32),
         ("split_col", c_int32),
+        ("scatter_col0", c_int32),
+        ("y2", c_void_p),
+        ("ldy2", c_int64),
+        ("y_split", c_int32),
         ("_pad1", c_int32),
     ]
 
@@ -560,11 +564,14 @@ def gemm_supported(m: int, n: int, k: int) -> bool:
 
 
 def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-         alpha: float = 1.0, scatter=None) -> torch.Tensor:
+         alpha: float = 1.0, scatter=None, out2: Optional[torch.Tensor] = None):
     """``out[M, N] = alpha * x[M, K] @ w[N, K].T (+ bias)`` with the hand-written sm_100a GEMM (see csa_gemm), same
-    layouts as ``linear``; batchable.  ``scatter = (pos, k_s, v_s, group_rows, dst_group_rows, split_col)`` fuses the
-    gather of the sampled key rows into the epilogue (w = [w_k; w_v]): a row ``r`` with ``pos[r % group_rows] >= 0``
-    is also stored into ``k_s`` / ``v_s`` at row ``(r // group_rows) * dst_group_rows + pos``."""
+    layouts as ``linear``; batchable.  ``scatter = (pos, k_s, v_s, group_rows, dst_group_rows, split_col[, col0])``
+    fuses the gather of the sampled key rows into the epilogue (w = [w_k; w_v], or [w_q; w_k; w_v] with ``col0 = C``):
+    a row ``r`` with ``pos[r % group_rows] >= 0`` is also stored into ``k_s`` / ``v_s`` at row
+    ``(r // group_rows) * dst_group_rows + pos``.  With ``out2`` the product is split by column: ``out`` takes the
+    first ``out.shape[1]`` columns, ``out2`` the rest (q and K|V of a stacked-weight GEMM in two buffers); returns
+    ``(out, out2)`` then."""
     _require_cuda(x, w)
     ensure_device(x.device)
     if x.dim() != 2 or w.dim() != 2 or x.stride(1) != 1 or w.stride(1) != 1 or x.shape[1] != w.shape[1] or \
@@ -572,7 +579,12 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         raise CsaNativeError("gemm expects 2-D x (M, K) and w (N, K) of one 16-bit dtype, unit column stride")
     m, k = x.shape
     n = w.shape[0]
-    if out is None:
+    if out2 is not None:
+        if out is None or out.dim() != 2 or out2.dim() != 2 or out.shape[0] != m or out2.shape[0] != m or \
+                out.shape[1] + out2.shape[1] != n or out.stride(1) != 1 or out2.stride(1) != 1 or \
+                out.dtype != x.dtype or out2.dtype != x.dtype:
+            raise CsaNativeError("gemm: out and out2 must be (M, n1) and (M, N - n1) of x's dtype, unit column stride")
+    elif out is None:
         out = torch.empty((m, n), dtype=x.dtype, device=x.device)
     elif out.shape != (m, n) or out.stride(1) != 1 or out.dtype != x.dtype:
         raise CsaNativeError("gemm: out must be (M, N) of x's dtype with unit column stride")
@@ -587,21 +599,24 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
             raise CsaNativeError("gemm: bias must be a contiguous (N,) tensor of x's dtype")
         a.bias = bias.data_ptr()
     a.y, a.ldy = out.data_ptr(), out.stride(0)
+    if out2 is not None:
+        a.y2, a.ldy2, a.y_split = out2.data_ptr(), out2.stride(0), out.shape[1]
     a.alpha = alpha
     if scatter is not None:
-        pos, k_s, v_s, group_rows, dst_group_rows, split_col = scatter
+        pos, k_s, v_s, group_rows, dst_group_rows, split_col = scatter[:6]
+        a.scatter_col0 = scatter[6] if len(scatter) > 6 else 0
         if pos.dtype != torch.int32 or not pos.is_contiguous() or pos.numel() < group_rows or \
                 k_s.dim() != 2 or k_s.stride(1) != 1 or v_s.shape != k_s.shape or v_s.stride(0) != k_s.stride(0) or \
-                k_s.dtype != x.dtype or k_s.shape[1] < split_col or k_s.shape[0] < (m // group_rows) * dst_group_rows:
+                k_s.dtype != x.dtype or k_s.shape[0] < (m // group_rows) * dst_group_rows:
             raise CsaNativeError("gemm: bad scatter buffers")
         a.scatter_pos, a.scatter_k, a.scatter_v = pos.data_ptr(), k_s.data_ptr(), v_s.data_ptr()
         a.scatter_ld, a.scatter_group_rows = k_s.stride(0), group_rows
         a.scatter_dst_group_rows, a.split_col = dst_group_rows, split_col
     lib = load()
     _issue(CSA_CALL_GEMM, a, lambda st: lib.csa_gemm(ctypes.byref(a), st), "csa_gemm", _stream_ptr(x), x,
-           keep=(x, w, bias, out, scatter))
+           keep=(x, w, bias, out, out2, scatter))
     LAUNCHES["csa_gemm"] += 1
-    return out
+    return out if out2 is None else (out, out2)
 
 
 def sample_positions(s_idx: torch.Tensor, s_count: torch.Tensor, n_cols: int,

@@ -79,6 +79,8 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                             # (N % 128 == 0, K % 64 == 0: every SDXL attn1 layer), else on cuBLASLt (csa_linear)
     gemm_qo = True          # to_q / to_out[0] on the hand-written GEMM too (False: cuBLASLt for those two, a few us
                             # faster per layer at F = 4 — profiles/r02_gemm.md — at the price of library launches)
+    fused_qkv = True        # to_q and to_k|to_v as ONE GEMM over the stacked weight [w_q; w_k; w_v] with two outputs
+                            # (q, and K|V where the id_bank keeps it): one launch less per layer, fewer partial waves
     fused_gather = True     # consistent write pass: the K|V projection's epilogue stores the sampled rows straight
                             # into K[S] / V[S] (no csa_gather_kv launch, no second pass over K and V)
     native_projections = True   # to_q / to_k|to_v (one GEMM) / to_out[0] issued by the library
@@ -198,15 +200,16 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
             native.begin_batch(x)
             try:
                 x2 = x.view(B * N, C)
-                q = self._proj(x2, plan[1])
-                # K and V in one GEMM: columns [0, C) and [C, 2C) — written straight into the bank arena's slot of
-                # this step when the write pass keeps K/V there.  The GEMM itself is issued once the branch is known
-                # (_attend_and_project): in the consistent write pass its epilogue also fills K[S] / V[S].
+                # q, and K and V side by side in one (rows, 2C) buffer — the bank arena's slot of this step when the
+                # write pass keeps K/V there.  The projections themselves are issued once the branch is known
+                # (_attend_and_project): one stacked-weight GEMM whose epilogue, in the consistent write pass, also
+                # fills K[S] / V[S].
+                q = torch.empty((B * N, C), dtype=x.dtype, device=x.device)
                 kv = self._arena_slot(cur_step, B * N, 2 * C, x) if write and self.bank_capacity else None
                 if kv is None:
                     kv = torch.empty((B * N, 2 * C), dtype=x.dtype, device=x.device)
                 k, v = kv[:, :C], kv[:, C:]
-                kv_job = (x2, plan[2], kv)
+                kv_job = (x2, plan, q, kv)
             except Exception:
                 native.abort_batch()
                 raise
@@ -274,7 +277,7 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
             st[1].clear()
 
     def _native_plan(self, attn, x):
-        """``(key, w_q, w_kv, w_out, b_out)`` when the attn module is the plain SDXL attn1 shape — bias-free Linear
+        """``(key, w_q, w_kv, w_out, b_out, w_qkv)`` when the attn module is the plain SDXL attn1 shape — bias-free Linear
         q/k/v, ``[Linear, Dropout]`` output with the dropout inactive, weights of x's dtype on x's device — else
         None (the module's own projections are used).  ``w_kv = cat(to_k.weight, to_v.weight)``.  Cached per attn
         module and re-validated cheaply: the weights' storage and version counters."""
@@ -301,10 +304,11 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
               and (bo is None or (bo.dtype == x.dtype and bo.is_contiguous())))
         if ok:
             native.flush_batch()     # torch.cat launches a kernel: nothing deferred may be overtaken
-            hit = (key, wq.detach(), torch.cat([wk.detach(), wv.detach()], dim=0).contiguous(), wo.detach(),
-                   None if bo is None else bo.detach())
+            w_qkv = torch.cat([wq.detach(), wk.detach(), wv.detach()], dim=0).contiguous()
+            hit = (key, w_qkv[:wq.shape[0]], w_qkv[wq.shape[0]:], wo.detach(), None if bo is None else bo.detach(),
+                   w_qkv)
         else:
-            hit = (key, None, None, None, None)
+            hit = (key, None, None, None, None, None)
         self.__dict__["_nplan"] = hit
         return hit if ok else None
 
@@ -336,9 +340,17 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
         o = torch.empty_like(q)
 
         def project_kv(scatter=None):
-            # the K|V projection of the current input, deferred until the branch is known (native path only)
-            if kv_job is not None:
-                self._proj(kv_job[0], kv_job[1], out=kv_job[2], scatter=scatter, kv=True)
+            # the q and K|V projections of the current input, deferred until the branch is known (native path only)
+            if kv_job is None:
+                return
+            x2, pl, q_out, kv_out = kv_job
+            if (self.native_gemm and self.fused_qkv and self.gemm_qo and pl[5] is not None
+                    and native.gemm_supported(x2.shape[0], 3 * C, C)):
+                sc = None if scatter is None else (scatter[0], scatter[1], scatter[2], scatter[3], scatter[4], 2 * C, C)
+                native.gemm(x2, pl[5], out=q_out, out2=kv_out, scatter=sc)
+            else:
+                self._proj(x2, pl[1], out=q_out)
+                self._proj(x2, pl[2], out=kv_out, scatter=scatter, kv=True)
 
         branch = "early"
         if cur_step < 5:                                        # :94-96

@@ -55,6 +55,25 @@ def test_gemm_alpha_strides_and_out():
     assert (y.float() - want).abs().max().item() <= 5e-3
 
 
+@pytest.mark.parametrize("m,C", [(8192, 1280), (4096, 640), (1000, 640)])
+def test_gemm_two_outputs_and_ragged_wide_tiles(m, C):
+    """Stacked weight [w_q; w_k; w_v] (N = 3C; 1920 is not a multiple of the 256-wide tile): q lands in `out`, K|V in
+    `out2`, both equal the separate products bit for bit."""
+    dtype = torch.bfloat16
+    g = torch.Generator(device=DEV).manual_seed(m + C)
+    x = torch.randn((m, C), device=DEV, generator=g).to(dtype)
+    w = (torch.randn((3 * C, C), device=DEV, generator=g) * C ** -0.5).to(dtype)
+    q = torch.full((m, C), 3.0, device=DEV, dtype=dtype)
+    kv = torch.full((m, 2 * C), 3.0, device=DEV, dtype=dtype)
+    native.gemm(x, w, out=q, out2=kv)
+    q_ref = native.gemm(x, w[:C])
+    kv_ref = native.gemm(x, w[C:])
+    torch.cuda.synchronize()
+    assert torch.equal(q, q_ref) and torch.equal(kv, kv_ref)
+    want = _ref(x, w, None, 1.0)
+    assert (torch.cat([q, kv], dim=1).float() - want).abs().max().item() <= 2e-2
+
+
 def test_gemm_rejects_bad_arguments():
     x = torch.zeros((128, 64), device=DEV, dtype=torch.bfloat16)
     w = torch.zeros((128, 64), device=DEV, dtype=torch.bfloat16)
@@ -89,8 +108,17 @@ def test_fused_gather_equals_gather_kv(Fl, N, C):
     v_s = torch.full((2 * cap, C), 7.0, device=DEV, dtype=dtype)
     kv = native.gemm(x, w_kv, scatter=(pos, k_s, v_s, Fl * N, cap, C))
     k_ref, v_ref, cap2 = native.gather_kv(kv[:, :C], kv[:, C:], Fl * N, 2, s_idx, s_count, Fl * N)
+    # the same through the stacked q|k|v weight with two outputs (what the processor issues)
+    w_q = (torch.randn((C, C), device=DEV, generator=g) * C ** -0.5).to(dtype)
+    k_s2 = torch.full((2 * cap, C), 7.0, device=DEV, dtype=dtype)
+    v_s2 = torch.full((2 * cap, C), 7.0, device=DEV, dtype=dtype)
+    q3 = torch.empty((2 * Fl * N, C), device=DEV, dtype=dtype)
+    kv3 = torch.empty((2 * Fl * N, 2 * C), device=DEV, dtype=dtype)
+    native.gemm(x, torch.cat([w_q, w_kv]).contiguous(), out=q3, out2=kv3,
+                scatter=(pos, k_s2, v_s2, Fl * N, cap, 2 * C, C))
     torch.cuda.synchronize()
     assert cap2 == cap
+    assert torch.equal(kv3, kv) and torch.equal(k_s2, k_s) and torch.equal(v_s2, v_s)
     for grp in range(2):
         assert torch.equal(k_s[grp * cap:grp * cap + cnt], k_ref[grp * cap:grp * cap + cnt])
         assert torch.equal(v_s[grp * cap:grp * cap + cnt], v_ref[grp * cap:grp * cap + cnt])

@@ -95,7 +95,7 @@ def test_native_projections_match_module_projections():
     want, trace_m = _story(False)
     assert [t[0] for t in trace_n] == [t[0] for t in trace_m] == ["early", "standard", "consistent", "early",
                                                                     "consistent"]
-    assert all(t[1] == 3 for t in trace_n), trace_n       # q, k|v, out: three library GEMMs per call
+    assert all(t[1] == 2 for t in trace_n), trace_n       # q|k|v (one stacked-weight GEMM), out: two GEMMs per call
     assert all(t[1] == 0 for t in trace_m), trace_m
     for a, b, t in zip(got, want, trace_n):
         err = (a - b).abs().max().item()
@@ -131,10 +131,10 @@ def test_native_layer_matches_oracle():
         random.seed(0)
         before = dict(native.LAUNCHES)
         got = proc(gattn, x.to(DEV, torch.bfloat16))
-    assert _gemms(native.LAUNCHES) - _gemms(before) == 3
-    # SDXL shapes run on the hand-written GEMM, and the consistent write pass needs no gather launch: the K|V
-    # projection's epilogue fills K[S] / V[S]
-    assert native.LAUNCHES["csa_gemm"] - before["csa_gemm"] == 3
+    assert _gemms(native.LAUNCHES) - _gemms(before) == 2
+    # SDXL shapes run on the hand-written GEMM (q|k|v in one launch, then out), and the consistent write pass needs
+    # no gather launch: the projection's epilogue fills K[S] / V[S]
+    assert native.LAUNCHES["csa_gemm"] - before["csa_gemm"] == 2
     assert native.LAUNCHES["csa_gather_kv"] == before["csa_gather_kv"]
     err, cos = max_abs_cos(got, want)
     assert err <= MAX_ABS and cos >= MIN_COS, f"max-abs {err:.3e} cos {cos:.6f}"

@@ -42,7 +42,10 @@ def main():
     shapes = [("32x32 q / out  F=4", 8192, 1280, 1280, False), ("32x32 k|v      F=4", 8192, 2560, 1280, False),
               ("64x64 q / out  F=4", 32768, 640, 640, True), ("64x64 k|v      F=4", 32768, 1280, 640, False),
               ("32x32 k|v      F=16", 32768, 2560, 1280, False), ("64x64 k|v      F=16", 131072, 1280, 640, False),
-              ("32x32 q  1 frame (N=8)", 1024, 1280, 1280, False), ("32x32 k|v read", 2048, 2560, 1280, False)]
+              ("32x32 q  1 frame (N=8)", 1024, 1280, 1280, False), ("32x32 k|v read", 2048, 2560, 1280, False),
+              ("32x32 q|k|v   F=4", 8192, 3840, 1280, False), ("64x64 q|k|v   F=4", 32768, 1920, 640, False),
+              ("32x32 q|k|v 2 frames (N=4)", 2048, 3840, 1280, False),
+              ("32x32 q|k|v 1 frame (N=8)", 1024, 3840, 1280, False)]
     rows = []
     for name, m, n, k, bias in shapes:
         rot = max(2, int(300e6 // ((m * k + m * n) * 2)) + 1)
