@@ -36,7 +36,12 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
+import contextlib
+import os
+
 from . import native
+
+_NULL = contextlib.nullcontext()
 
 
 def _export_tensor(t: torch.Tensor):
@@ -227,6 +232,10 @@ class FrameSharding:
             raise ValueError("exchange must be 'p2p' (fused gather + peer-memory scatter) or 'nccl' (all-gather)")
         self.exchange = exchange
         self.mask_sync = "broadcast"   # or "seeded": see sync_sample()
+        # SMs the attention launch leaves to a CONCURRENT peer scatter on a side stream (0 = the scatter runs before
+        # the attention launch on the same stream).  CSA_OVERLAP_SMS overrides (tuning).
+        self.overlap_sms = int(os.environ.get("CSA_OVERLAP_SMS", "0"))
+        self._side_streams = {}
         self.peers: Optional[PeerExchange] = None
         if not dist.is_initialized():
             raise RuntimeError("FrameSharding needs an initialised torch.distributed process group")
@@ -365,12 +374,27 @@ class FrameSharding:
         ex.epoch += 1
         epoch = ex.epoch
         ks, vs = ex.views(epoch % ex.SLOTS, rows, C, k.dtype)
-        # Geometry stays on the device (no read-back of the sampled counts): the scatter kernel finds this rank's run
-        # of S in `ranges`, the attention kernel the peers' bounds.  Peers last read this slot in epoch - SLOTS.
-        native.peer_scatter_kv(k, v, pl.s_idx, fr * N, 0, ks, vs, ex.ready(), me, epoch,
-                               ex.done()[me], epoch - ex.SLOTS, ex.counter(),
-                               ranges=pl.ranges, frames_per_peer=fr, idx_adjust=-self.f0 * N,
-                               epoch_base=ex.epoch_base)
+        # Geometry stays on the device (no read-back of the sampled counts): the scatter kernel finds this rank's run of
+        # S in `ranges`, the attention kernel the peers' bounds.  Peers last read this slot in epoch - SLOTS.
+        #
+        # The scatter runs on a SIDE stream, concurrently with the attention launch: the attention kernel does not
+        # depend on the scatter's completion but on the arrival flags (its own rows' flag included), starts on each
+        # frame's own — local — block, and leaves `overlap_sms` SMs free so that the scatter's CTAs always have
+        # somewhere to run (a persistent attention launch that filled every SM while waiting for flags would
+        # otherwise starve the very kernel that raises them).  Measured: the scatter is 21-35 us (F=4) / 58-104 us
+        # (F=16) per layer over real links (profiles/r02v_peer_scatter_nvlink.md), ~10 % of a step when exposed.
+        side = None
+        if self.overlap_sms > 0 and q.is_cuda:
+            native.flush_batch()                   # the projections are on the main stream from here
+            main = torch.cuda.current_stream(q.device)
+            side = self._side_stream(q.device)
+            side.wait_stream(main)
+        ctx = torch.cuda.stream(side) if side is not None else _NULL
+        with ctx:
+            native.peer_scatter_kv(k, v, pl.s_idx, fr * N, 0, ks, vs, ex.ready(), me, epoch,
+                                   ex.done()[me], epoch - ex.SLOTS, ex.counter(),
+                                   ranges=pl.ranges, frames_per_peer=fr, idx_adjust=-self.f0 * N,
+                                   epoch_base=ex.epoch_base)
         sent = self._p2p_sent.setdefault(id(pl.cm), [pl, 0])   # per mask object (masks are re-sampled in place)
         sent[0] = pl
         sent[1] += (self.gc - 1) * 2 * C * k.element_size()
@@ -378,9 +402,23 @@ class FrameSharding:
                         k_a=ks[me], v_a=vs[me], a_group_rows=rows, ranges=pl.ranges, range_base=self.f0,
                         range_step=1, k_b=k, v_b=v, b_group_rows=fr * N, cb=(0, N, N),
                         b_first=True, ready=ex.ready()[me], ready_epoch=epoch, ready_peers=self.gc,
-                        ready_frames_per_peer=fr, epoch_base=ex.epoch_base)
+                        ready_frames_per_peer=fr, epoch_base=ex.epoch_base,
+                        max_ctas=(self._sm_count(q.device) - self.overlap_sms) if side is not None else 0)
+        if side is not None:
+            native.flush_batch()
+            torch.cuda.current_stream(q.device).wait_stream(side)   # join: k / v may be reused after this call
         native.peer_signal(ex.done(), me, epoch, q, epoch_base=ex.epoch_base)
         return o
+
+    def _side_stream(self, device):
+        st = self._side_streams.get(device.index)
+        if st is None:
+            st = self._side_streams[device.index] = torch.cuda.Stream(device)
+        return st
+
+    @staticmethod
+    def _sm_count(device) -> int:
+        return torch.cuda.get_device_properties(device).multi_processor_count
 
     def end_step(self) -> None:
         """Called by the processor at the step roll-over (every rank makes the same calls)."""
