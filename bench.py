@@ -310,6 +310,8 @@ class Workload:
         cls.native_projections = not args.module_projections
         cls.native_gemm = args.projections != "cublaslt"
         cls.gemm_qo = args.projections == "own"
+        cls.fused_gather = not args.no_fused_gather
+        cls.fused_qkv = not args.no_fused_qkv
         self.sharding = None
         units_local = 2 * Fl
         if world > 1:
@@ -920,6 +922,9 @@ def main():
     ap.add_argument("--projections", choices=["own", "mixed", "cublaslt"], default="own",
                     help="own: every projection on the hand-written sm_100a GEMM (K|V with the fused gather); mixed: "
                          "only K|V (q / out on cuBLASLt); cublaslt: library GEMMs + csa_gather_kv (round-1 path)")
+    ap.add_argument("--no-fused-gather", action="store_true",
+                    help="own projections: csa_gather_kv as a separate launch instead of the K|V epilogue's fused gather")
+    ap.add_argument("--no-fused-qkv", action="store_true", help="own projections: q and K|V as two GEMM launches")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="issue every step call by call from Python instead of replaying one CUDA graph per step")
     ap.add_argument("--no-hbm", action="store_true", help="skip the HBM-bound kernels' roofline entries")

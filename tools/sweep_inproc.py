@@ -63,7 +63,7 @@ def main():
             for sa in a.sas:
                 args = argparse.Namespace(res=res, sa=sa, placement=a.placement, module_projections=False,
                                           exchange=a.exchange, share_weights=True, graph=a.graph, frames=F,
-                                          projections="own")
+                                          projections="own", no_fused_gather=False, no_fused_qkv=False)
                 try:
                     wl = bench.Workload(args, F, dev, dtype, world, rank, shard_cache)
                     with torch.no_grad():
