@@ -798,52 +798,84 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         tc_fence_before();
       } else {
         // piece of a split unit: leave the unnormalised partial (O, m, l) of this row in the workspace; the CTA
-        // that delivers the last piece of the unit (arrival counter) merges all of them — nobody waits for anybody
+        // that delivers the last piece of the unit (arrival counter) merges all of them — nobody waits for anybody.
+        // A partial = [16 column chunks][256 rows] float4 of O (a warp touches 512 contiguous bytes), [256] m, [256] l.
         const int prow = s * kBM + row;
+        const int my = e.piece % p.split;
         float* part = p.ws + static_cast<int64_t>(e.piece) * kPieceFloats;
-        if (nt > 0) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t ov[32];
-            tmem_ld32(tO + c * 32, ov);
-            tc_wait_ld();
-            uint4* dst = reinterpret_cast<uint4*>(part + prow * kHD + c * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) __stcg(dst + i, make_uint4(ov[4 * i], ov[4 * i + 1], ov[4 * i + 2], ov[4 * i + 3]));
-          }
-          tc_fence_before();
-        }
-        __stcg(part + 2 * kBM * kHD + prow, m);
-        __stcg(part + 2 * kBM * kHD + 2 * kBM + prow, l);
-        __threadfence();
-        named_bar_sync(9, kThreads - 128);  // all softmax threads of the CTA have published their rows
-        if (threadIdx.x == 128) {
-          const uint32_t prev = atomicAdd(p.ws_count + e.split_unit, 1u);
-          const bool last = prev == static_cast<uint32_t>(p.split) - 1u;
-          if (last) p.ws_count[e.split_unit] = 0u;  // ready for the next launch
-          sm.merge_flag = last ? 1u : 0u;
-        }
+        const float* base = p.ws + static_cast<int64_t>(e.piece - my) * kPieceFloats;
+        // If every other piece has already been delivered this CTA is the one that merges, and it does so straight
+        // from TMEM and registers: no partial of its own is written and read back.
+        if (threadIdx.x == 128)
+          sm.merge_flag = ld_acquire_sys(p.ws_count + e.split_unit) == static_cast<uint32_t>(p.split) - 1u ? 2u : 0u;
         named_bar_sync(9, kThreads - 128);
-        if (sm.merge_flag != 0u) {
+        const bool direct = sm.merge_flag == 2u;
+        bool merge = direct;
+        if (!direct) {
+          if (nt > 0) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t ov[32];
+              tmem_ld32(tO + c * 32, ov);
+              tc_wait_ld();
+              float4* dst = reinterpret_cast<float4*>(part) + (c * 8) * (2 * kBM) + prow;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                __stcg(dst + i * (2 * kBM), make_float4(__uint_as_float(ov[4 * i]), __uint_as_float(ov[4 * i + 1]),
+                                                        __uint_as_float(ov[4 * i + 2]), __uint_as_float(ov[4 * i + 3])));
+            }
+            tc_fence_before();
+          }
+          __stcg(part + 2 * kBM * kHD + prow, m);
+          __stcg(part + 2 * kBM * kHD + 2 * kBM + prow, l);
           __threadfence();
-          const float* base = p.ws + static_cast<int64_t>(e.piece - (e.piece % p.split)) * kPieceFloats;
-          float mm = -INFINITY;
+          named_bar_sync(9, kThreads - 128);  // all softmax threads of the CTA have published their rows
+          if (threadIdx.x == 128) {
+            const uint32_t prev = atomicAdd(p.ws_count + e.split_unit, 1u);
+            sm.merge_flag = prev == static_cast<uint32_t>(p.split) - 1u ? 1u : 0u;
+          }
+          named_bar_sync(9, kThreads - 128);
+          merge = sm.merge_flag != 0u;
+        }
+        if (merge) {
+          __threadfence();
+          if (threadIdx.x == 128) p.ws_count[e.split_unit] = 0u;  // ready for the next launch
+          const bool own = direct && nt > 0 && l > 0.f;  // this thread's row is still on chip
+          float mm = own ? m : -INFINITY;
           for (int i = 0; i < p.split; ++i)
-            mm = fmaxf(mm, __ldcg(base + static_cast<int64_t>(i) * kPieceFloats + 2 * kBM * kHD + prow));
+            if (!(direct && i == my))
+              mm = fmaxf(mm, __ldcg(base + static_cast<int64_t>(i) * kPieceFloats + 2 * kBM * kHD + prow));
+          // pieces are accumulated in index order whoever merges (the result does not depend on the arrival order)
           float acc[kHD];
 #pragma unroll
           for (int c = 0; c < kHD; ++c) acc[c] = 0.f;
           float lsum = 0.f;
           for (int i = 0; i < p.split; ++i) {
+            if (direct && i == my) {
+              if (own) {
+                const float wgt = fast_exp2(m - mm);
+                lsum += wgt * l;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  uint32_t ov[32];
+                  tmem_ld32(tO + c * 32, ov);
+                  tc_wait_ld();
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) acc[c * 32 + j] += wgt * __uint_as_float(ov[j]);
+                }
+                tc_fence_before();
+              }
+              continue;
+            }
             const float* pi = base + static_cast<int64_t>(i) * kPieceFloats;
             const float li = __ldcg(pi + 2 * kBM * kHD + 2 * kBM + prow);
             if (li > 0.f) {  // a piece without key tiles contributes nothing (its O rows were never written)
               const float wgt = fast_exp2(__ldcg(pi + 2 * kBM * kHD + prow) - mm);
               lsum += wgt * li;
-              const float4* src = reinterpret_cast<const float4*>(pi + prow * kHD);
+              const float4* src = reinterpret_cast<const float4*>(pi) + prow;
 #pragma unroll
               for (int c = 0; c < kHD / 4; ++c) {
-                const float4 x = __ldcg(src + c);
+                const float4 x = __ldcg(src + c * (2 * kBM));
                 acc[4 * c + 0] += wgt * x.x;
                 acc[4 * c + 1] += wgt * x.y;
                 acc[4 * c + 2] += wgt * x.z;

@@ -28,7 +28,7 @@ def run(F, N, C, heads, sa=0.5, dtype=torch.bfloat16, iters=20):
     k_s, v_s, cap = native.gather_kv(k, v, F * N, 2, s_idx, s_count, F * N)
     fn = lambda: native.attn_fwd(q, o, heads=heads, n_groups=2, n_frames=F, n_q=N, k_a=k_s, v_a=v_s,
                                  a_group_rows=cap, ranges=ranges, range_base=0, range_step=1, k_b=k, v_b=v,
-                                 b_group_rows=F * N, cb=(0, N, N))
+                                 b_group_rows=F * N, cb=(0, N, N), split=os.environ.get('CSA_NO_SPLIT') != '1')
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
