@@ -676,6 +676,11 @@ def run_b200_arm(args):
                            "unit": UNIT, "ms_per_step": round(e2e["ms"] / steps, 4),
                            "h2d_bytes_per_step": e2e["h2d"] * world, "d2h_bytes_per_step": e2e["d2h"] * world,
                            "issue": e2e["mode"]}
+            if e2e.get("link"):
+                lk = e2e["link"]
+                line["e2e"]["link"] = lk
+                line["e2e"]["link_floor_ms_per_step"] = round(
+                    max(e2e["h2d"], e2e["d2h"]) / (lk["both_GBps_per_direction"] * 1e9) * 1e3, 3)
         if world == 1 and not args.no_cpu:
             base = cpu_reference_sample(args, steps=3, warmup=1, whole_step=False)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample")}
@@ -698,7 +703,8 @@ def run_e2e(args, wl, dev, barrier, rank):
     h2d = sum(x.numel() * x.element_size() for x in host_in)
     d2h = sum(x.numel() * x.element_size() for x in host_out)
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    depth = 3
+    depth = max(2, args.e2e_depth)
+    ahead = depth - 1
     shapes = sorted({tuple(x.shape) for x in hidden})
     ring = {s: [torch.empty(s, device=dev, dtype=hidden[0].dtype) for _ in range(depth)] for s in shapes}
     n = len(hidden)
@@ -728,12 +734,11 @@ def run_e2e(args, wl, dev, barrier, rank):
             ready[i] = ev
             slots[i] = (s, k)
 
-        issue_h2d(0)
-        if n > 1:
-            issue_h2d(1)
+        for i in range(min(ahead, n)):
+            issue_h2d(i)
         for i in range(n):
-            if i + 2 < n:
-                issue_h2d(i + 2)
+            if i + ahead < n:
+                issue_h2d(i + ahead)
             main.wait_event(ready[i])
             s, k = slots[i]
             out = procs[i](attns[i], ring[s][k])
@@ -783,7 +788,40 @@ def run_e2e(args, wl, dev, barrier, rank):
             graph.replay() if graph is not None else e2e_step()
         e1.record()
         barrier()
-    return {"ms": e0.elapsed_time(e1), "h2d": h2d, "d2h": d2h, "mode": mode}
+        link = measure_link(host_in, host_out, dev, s_in, s_out) if rank == 0 else None
+    return {"ms": e0.elapsed_time(e1), "h2d": h2d, "d2h": d2h, "mode": mode, "link": link}
+
+
+def measure_link(host_in, host_out, dev, s_in, s_out):
+    """What the host link gives on this box with the e2e leg's own pinned buffers and nothing else running: H2D alone,
+    D2H alone, both at once (GB/s per direction) — the floor of the e2e step is bytes / the concurrent rate."""
+    dst = [torch.empty(x.shape, device=dev, dtype=x.dtype) for x in host_in[:8]]
+    nbytes = sum(x.numel() * x.element_size() for x in host_in[:8])
+
+    def run(do_in, do_out):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        main = torch.cuda.current_stream(dev)
+        e0.record(main)
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        for _ in range(3):
+            for d, hi, ho in zip(dst, host_in, host_out):
+                if do_in:
+                    with torch.cuda.stream(s_in):
+                        d.copy_(hi, non_blocking=True)
+                if do_out:
+                    with torch.cuda.stream(s_out):
+                        ho.copy_(d, non_blocking=True)
+        main.wait_stream(s_in)
+        main.wait_stream(s_out)
+        e1.record(main)
+        torch.cuda.synchronize()
+        return 3 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    run(True, True)
+    return {"h2d_alone_GBps": round(run(True, False), 1), "d2h_alone_GBps": round(run(False, True), 1),
+            "both_GBps_per_direction": round(run(True, True), 1)}
 
 
 def hbm_kernels(args, wl, dev):
@@ -907,6 +945,8 @@ def main():
                     help="up: the reference's placement (36 up-block attn1 layers); all: all 70 attn1 layers")
     ap.add_argument("--dtype", choices=["bf16", "fp16"], default="bf16")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-depth", type=int, default=3,
+                    help="e2e leg: device slots per latent shape (the H2D copies run depth-1 layers ahead)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p",
                     help="N >= 4: how the sampled K/V rows travel between the GPUs of a CFG half (spider_b200/dist.py)")
