@@ -4,21 +4,27 @@
 // are read where the module keeps them (both operands are K-major: exactly the Q K^T operand shape of the attention
 // kernel).  Replaces the cuBLASLt calls of csa_linear for the shapes of the path (K % 64 == 0, N % 128 == 0).
 //
-// Persistent CTAs (one per SM, 192 threads) in CLUSTERS OF TWO, warp-specialised:
-//   warp 0      TMA producer: per 64-wide k-block its own 128 x 64 tile of x, and HALF of the BN x 64 tile of w,
-//               multicast to both CTAs of the cluster (the two CTAs work on vertically adjacent output tiles, i.e.
-//               the same rows of w).  With 128 x 128 tiles and no sharing the kernel is bound by the L2 -> SM fabric
-//               (32 KB of operands per 256 tensor-clocks and SM = 3x the ~6300 B/clk the L2 delivers chip-wide:
-//               measured 11.4 TB/s of operand traffic, 730 TFLOP/s); 128 x 256 tiles with the w tile shared need
-//               64 B/clk per SM.
-//   warp 1      TMEM allocator + MMA issue: tcgen05.mma kind::f16, M128 N{256,128} K16, four per k-block; two
-//               accumulators (2 x BN TMEM columns) so that the epilogue of tile i overlaps the main loop of i+1.
-//               A stage is released to BOTH producers of the cluster (multicast commit): the peer writes into it too.
-//   warps 2-5   epilogue: tcgen05.ld (thread == output row), alpha / bias, 16-bit pack, 16-byte stores; and the FUSED
-//               K/V GATHER of the consistent-attention write pass: a row whose position in the sampled key list S is
-//               known (`scatter_pos[row] >= 0`, csa_sample_positions) is also stored, in S order, into the K[S] / V[S]
+// Persistent CTAs (one per SM, 192 threads) in CLUSTERS OF TWO = one CTA PAIR on the two SMs of a TPC, warp-specialised.
+// With 128 x 128 tiles and nothing shared the kernel is bound by the L2 -> SM fabric (32 KB of operands per 256
+// tensor-clocks and SM: measured 11.4 TB/s of operand traffic, 730 TFLOP/s).  Two forms of sharing the w tile:
+//   * 256-wide tiles: ONE tcgen05.mma.cta_group::2 of M = 256, N = 256 per 16-wide k step, issued by the pair's leader:
+//     each CTA holds its own 128 rows of x and HALF of the w tile's rows in shared memory (32 KB per stage instead
+//     of 48: six stages instead of four, and a third less shared-memory read traffic per FLOP), its own 128 x 256
+//     accumulator in TMEM.  Both producers credit the leader's `full` barrier (cta_group::2 TMA loads), the leader's
+//     commits free the stage and publish the accumulator in both CTAs (multicast), and both CTAs' epilogue warps
+//     release the accumulator on the leader's barrier.  q|k|v of the 32x32 layer: 58.4 us, 0.84 of the cuBLAS-measured
+//     peak (cuBLASLt on the same shape: 63.1 us); before, with two M = 128 MMAs and the w tile multicast: 63.9 us.
+//   * 128-wide tiles (N % 256 != 0 and too ragged for 256): two M = 128 MMAs, each CTA loads half of the w tile and
+//     multicasts it to both.
+//   warp 0      TMA producer
+//   warp 1      TMEM allocator + MMA issue: four k steps per 64-wide k-block; two accumulators (2 x BN TMEM columns)
+//               so that the epilogue of tile i overlaps the main loop of i+1.
+//   warps 2-5   epilogue: tcgen05.ld (thread == output row), alpha / bias, 16-bit pack, staged through shared memory so
+//               that every store instruction writes whole 128-byte lines; and the FUSED K/V GATHER of the
+//               consistent-attention write pass: a row whose position in the sampled key list S is known
+//               (`scatter_pos[row] >= 0`, csa_sample_positions) is also stored, in S order, into the K[S] / V[S]
 //               buffer pair the attention kernel streams — the separate csa_gather_kv launch and its re-read of K and V
-//               from HBM disappear (2.3 % of the denoise step).
+//               from HBM disappear.
 // Tile pairs are dealt round-robin to the clusters, n fastest: clusters that run at the same time share their x
 // tiles through L2.
 #include <cuda_fp16.h>
@@ -37,17 +43,19 @@ constexpr int kGSmemBudget = 196608;    // operand ring
 constexpr int kStageRow = 144;          // 128 bytes of a row's 64 columns + 16 bytes of padding (bank-conflict free)
 constexpr int kStageBytes = 32 * kStageRow;
 
-template <int kBN>
+// k2Sm: the CTA pair runs one M = 256 MMA (cta_group::2) and each CTA keeps only ITS half of the w tile's rows;
+// otherwise two M = 128 MMAs, each CTA holding the whole w tile (the halves are multicast).
+template <int kBN, bool k2Sm>
 struct GemmCfg {
-  static constexpr int kTileB = kBN * kGK * 2;
-  static constexpr int kStages = kGSmemBudget / (kGTileA + kTileB);   // 4 (BN = 256) or 6 (BN = 128)
+  static constexpr int kTileB = (k2Sm ? kBN / 2 : kBN) * kGK * 2;
+  static constexpr int kStages = kGSmemBudget / (kGTileA + kTileB);   // 4 / 6 (BN = 256 / 128), 6 / 8 with k2Sm
 };
 
-template <int kBN>
+template <int kBN, bool k2Sm>
 struct __align__(1024) GemmSmem {
-  uint8_t a[GemmCfg<kBN>::kStages][kGTileA];
-  uint8_t b[GemmCfg<kBN>::kStages][GemmCfg<kBN>::kTileB];
-  uint64_t full[GemmCfg<kBN>::kStages], empty[GemmCfg<kBN>::kStages];
+  uint8_t a[GemmCfg<kBN, k2Sm>::kStages][kGTileA];
+  uint8_t b[GemmCfg<kBN, k2Sm>::kStages][GemmCfg<kBN, k2Sm>::kTileB];
+  uint64_t full[GemmCfg<kBN, k2Sm>::kStages], empty[GemmCfg<kBN, k2Sm>::kStages];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
   alignas(16) uint8_t stage[4][kStageBytes];   // epilogue staging, one block of 32 rows x 128 B (+ pad) per epilogue warp
@@ -76,12 +84,13 @@ struct GemmParams {
 
 #define GSB(field) (sb + static_cast<uint32_t>(offsetof(Smem, field)))
 
-template <bool kBF16, int kBN, int kCl>
+template <bool kBF16, int kBN, bool k2Sm>
 __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int kCl = 2;
   constexpr uint16_t kMask = static_cast<uint16_t>((1u << kCl) - 1u);
-  using Smem = GemmSmem<kBN>;
-  constexpr int kStages = GemmCfg<kBN>::kStages;
-  constexpr int kTileB = GemmCfg<kBN>::kTileB;
+  using Smem = GemmSmem<kBN, k2Sm>;
+  constexpr int kStages = GemmCfg<kBN, k2Sm>::kStages;
+  constexpr int kTileB = GemmCfg<kBN, k2Sm>::kTileB;
   extern __shared__ uint8_t smem_raw[];
   // the dynamic shared-memory window starts at the same offset in both CTAs of the cluster, so rounding it up gives
   // the same offsets too (multicast loads and commits address the peer by offset)
@@ -98,15 +107,19 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
     tma_prefetch_desc(&p.tm_w);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(GSB(full) + 8u * i, 1);
-      mbar_init(GSB(empty) + 8u * i, kCl);  // every MMA warp of the cluster has consumed the stage
+      // every MMA warp of the cluster has consumed the stage (k2Sm: the leader's commit arrives once in each CTA)
+      mbar_init(GSB(empty) + 8u * i, k2Sm ? 1 : kCl);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(GSB(acc_full) + 8u * i, 1);
-      mbar_init(GSB(acc_empty) + 8u * i, 4);  // one arrival per epilogue warp
+      // one arrival per epilogue warp (k2Sm: of both CTAs, on the leader's barrier — its MMA writes both accumulators)
+      mbar_init(GSB(acc_empty) + 8u * i, k2Sm ? 8 : 4);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<2 * kBN>(GSB(tmem_base));
+  if (warp == 1) {
+    if constexpr (k2Sm) tmem_alloc_2sm<2 * kBN>(GSB(tmem_base)); else tmem_alloc<2 * kBN>(GSB(tmem_base));
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();    // the peer's barriers exist before anything of ours can reach them
@@ -124,22 +137,31 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
         const int m0 = ((t / p.tiles_n) * kCl + static_cast<int>(crank)) * kGM, n0 = (t % p.tiles_n) * kBN;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(GSB(empty) + 8u * st, ph ^ 1, 0x500, p.dbg);
-          mbar_arrive_expect_tx(GSB(full) + 8u * st, kGTileA + kTileB);   // x tile + every slice of the w tile
-          tma_load_2d(&p.tm_x, GSB(a) + static_cast<uint32_t>(kGTileA) * st, GSB(full) + 8u * st, kb * kGK, m0);
-          // my slice of the w tile (rows [n0 + rank * BN/kCl, + BN/kCl)) goes to every CTA, at the slice's place
-          tma_load_2d_mc(&p.tm_w, GSB(b) + static_cast<uint32_t>(kTileB) * st + crank * (kTileB / kCl),
-                         GSB(full) + 8u * st, kb * kGK, n0 + static_cast<int>(crank) * (kBN / kCl), kMask);
+          if constexpr (k2Sm) {
+            // both CTAs' tiles are credited to the leader's barrier: its MMA consumes both
+            if (crank == 0) mbar_arrive_expect_tx(GSB(full) + 8u * st, 2 * (kGTileA + kTileB));
+            tma_load_2d_2sm(&p.tm_x, GSB(a) + static_cast<uint32_t>(kGTileA) * st, GSB(full) + 8u * st, kb * kGK, m0);
+            // my half of the w tile's rows stays here
+            tma_load_2d_2sm(&p.tm_w, GSB(b) + static_cast<uint32_t>(kTileB) * st, GSB(full) + 8u * st, kb * kGK,
+                            n0 + static_cast<int>(crank) * (kBN / 2));
+          } else {
+            mbar_arrive_expect_tx(GSB(full) + 8u * st, kGTileA + kTileB);   // x tile + every slice of the w tile
+            tma_load_2d(&p.tm_x, GSB(a) + static_cast<uint32_t>(kGTileA) * st, GSB(full) + 8u * st, kb * kGK, m0);
+            // my slice of the w tile (rows [n0 + rank * BN/kCl, + BN/kCl)) goes to every CTA, at the slice's place
+            tma_load_2d_mc(&p.tm_w, GSB(b) + static_cast<uint32_t>(kTileB) * st + crank * (kTileB / kCl),
+                           GSB(full) + 8u * st, kb * kGK, n0 + static_cast<int>(crank) * (kBN / kCl), kMask);
+          }
           if (++st == kStages) { st = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================================================================================ MMA issue
-    constexpr uint32_t idesc = make_idesc(kGM, kBN, kBF16 ? 1 : 0, 0, 0);
+    constexpr uint32_t idesc = make_idesc(k2Sm ? 2 * kGM : kGM, kBN, kBF16 ? 1 : 0, 0, 0);
     int st = 0;
     uint32_t ph = 0, aph[2] = {0, 0};
     int it = 0;
-    for (int t = cluster_id; t < n_items; t += n_clusters, ++it) {
+    for (int t = cluster_id; t < n_items && !(k2Sm && crank != 0); t += n_clusters, ++it) {
       const int buf = it & 1;
       // the epilogue has drained this accumulator (first use of each buffer: nothing to wait for)
       if (it >= 2) {
@@ -154,10 +176,17 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
         const uint64_t da = make_sw128_desc(GSB(a) + static_cast<uint32_t>(kGTileA) * st);
         const uint64_t db = make_sw128_desc(GSB(b) + static_cast<uint32_t>(kTileB) * st);
         if (elect_one()) {
+          if constexpr (k2Sm) {
 #pragma unroll
-          for (int kk = 0; kk < kGK / 16; ++kk) mma_ss(tacc, da + kk * 2, db + kk * 2, idesc, (kb | kk) ? 1u : 0u);
-          tc_commit_mc(GSB(empty) + 8u * st, kMask);  // free the stage in every CTA of the cluster
-          if (kb == kblocks - 1) tc_commit(GSB(acc_full) + 8u * buf);
+            for (int kk = 0; kk < kGK / 16; ++kk) mma_ss_2sm(tacc, da + kk * 2, db + kk * 2, idesc, (kb | kk) ? 1u : 0u);
+            tc_commit_2sm(GSB(empty) + 8u * st);                        // free the stage in both CTAs
+            if (kb == kblocks - 1) tc_commit_2sm(GSB(acc_full) + 8u * buf);  // both CTAs' epilogues
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < kGK / 16; ++kk) mma_ss(tacc, da + kk * 2, db + kk * 2, idesc, (kb | kk) ? 1u : 0u);
+            tc_commit_mc(GSB(empty) + 8u * st, kMask);  // free the stage in every CTA of the cluster
+            if (kb == kblocks - 1) tc_commit(GSB(acc_full) + 8u * buf);
+          }
         }
         __syncwarp();
         if (++st == kStages) { st = 0; ph ^= 1; }
@@ -269,7 +298,9 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
       // this accumulator may be overwritten by the main loop of the tile after next
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(GSB(acc_empty) + 8u * buf);
+      if (lane == 0) {
+        if constexpr (k2Sm) mbar_arrive_cluster(GSB(acc_empty) + 8u * buf, 0); else mbar_arrive(GSB(acc_empty) + 8u * buf);
+      }
     }
   }
 
@@ -277,7 +308,7 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
   cluster_sync_all();    // nobody leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<2 * kBN>(tmem);
+    if constexpr (k2Sm) tmem_dealloc_2sm<2 * kBN>(tmem); else tmem_dealloc<2 * kBN>(tmem);
   }
 }
 
@@ -319,16 +350,17 @@ extern "C" int csa_gemm_supported(int64_t m, int64_t n, int64_t k) {
   return (m > 0 && n > 0 && k > 0 && (n % 128) == 0 && (k % kGK) == 0 && m < (1ll << 30) && n < (1ll << 30)) ? 1 : 0;
 }
 
-template <int kBN, int kCl>
+template <int kBN, bool k2Sm>
 static int gemm_launch(const csa_gemm_args_t* a, GemmParams& p, int dev, int sms, void* stream) {
+  constexpr int kCl = 2;
   int rc;
   if ((rc = gemm_encode(&p.tm_x, a->dtype, a->x, a->m, a->k, a->ldx, kGM))) return rc;
   if ((rc = gemm_encode(&p.tm_w, a->dtype, a->w, a->n, a->k, a->ldw, kBN / kCl))) return rc;
   p.pairs_m = static_cast<int32_t>((a->m + kCl * kGM - 1) / (kCl * kGM));
   p.tiles_n = static_cast<int32_t>((a->n + kBN - 1) / kBN);   // a ragged last tile reads zero rows of w (TMA OOB fill)
   const int n_items = p.pairs_m * p.tiles_n;
-  const size_t smem = sizeof(GemmSmem<kBN>) + 1024;
-  auto kern = a->dtype == CSA_DTYPE_BF16 ? csa_gemm_kernel<true, kBN, kCl> : csa_gemm_kernel<false, kBN, kCl>;
+  const size_t smem = sizeof(GemmSmem<kBN, k2Sm>) + 1024;
+  auto kern = a->dtype == CSA_DTYPE_BF16 ? csa_gemm_kernel<true, kBN, k2Sm> : csa_gemm_kernel<false, kBN, k2Sm>;
   static bool smem_set[64][2];
   static int max_clusters[64][2];
   const int ki = a->dtype == CSA_DTYPE_BF16 ? 1 : 0;
@@ -431,15 +463,19 @@ extern "C" int csa_gemm(const csa_gemm_args_t* a, void* stream) {
   // (N = 1920: yes; N = 640: no — measured 45.5 us wide vs 42.0 us narrow)
   const int64_t tiles_wide = (a->n + 255) / 256;
   const bool wide = tiles_wide * 256 * 8 <= a->n * 9 && blocks_m * tiles_wide >= sms / 2;
-  // CSA_GEMM_CLUSTER=4: four CTAs stacked along M share one w tile instead of two (tuning knob; measured no faster on
-  // any shape of the path — 132 instead of 148 SMs can hold clusters of four — profiles/r02_gemm.md)
-  static const int cl_env = []() {
-    const char* e = getenv("CSA_GEMM_CLUSTER");
-    return e ? atoi(e) : 0;
+  // CSA_GEMM_2SM=0: two M = 128 MMAs with the w tile multicast instead of one M = 256 MMA of the CTA pair (A/B knob)
+  static const bool two_sm = []() {
+    const char* e = getenv("CSA_GEMM_2SM");
+    return !(e && atoi(e) == 0);
   }();
-  const bool four = cl_env == 4;
-  if (wide) return four ? gemm_launch<256, 4>(a, p, dev, sms, stream) : gemm_launch<256, 2>(a, p, dev, sms, stream);
-  return four ? gemm_launch<128, 4>(a, p, dev, sms, stream) : gemm_launch<128, 2>(a, p, dev, sms, stream);
+  if (wide) return two_sm ? gemm_launch<256, true>(a, p, dev, sms, stream) : gemm_launch<256, false>(a, p, dev, sms, stream);
+  // 128-wide tiles stay on the multicast form: the pair MMA with N = 128 measured slower (41.6 vs 37.5 us on
+  // 32768 x 640 x 640; CSA_GEMM_2SM=2 forces it)
+  static const bool two_sm_narrow = []() {
+    const char* e = getenv("CSA_GEMM_2SM");
+    return e && atoi(e) == 2;
+  }();
+  return two_sm_narrow ? gemm_launch<128, true>(a, p, dev, sms, stream) : gemm_launch<128, false>(a, p, dev, sms, stream);
 }
 
 extern "C" int csa_sample_positions(const int32_t* s_idx, const int32_t* s_count, int32_t n_cols, int32_t* pos,

@@ -162,6 +162,52 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
       "h"(cta_mask)
       : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster, on the two SMs of a TPC, run ONE tcgen05.mma of M = 256: each
+// holds its own 128 rows of A and HALF of B's rows in shared memory, its own 128 rows of D in tensor memory; the
+// leader (cluster rank 0) issues.  All of these are executed as described per function.
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst) {   // one warp of EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {    // same warps, after a cluster barrier
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// 2-D tiled load into THIS CTA's shared memory whose byte count is credited to the mbarrier at the same offset in the
+// pair's leader CTA (bit 24 of a shared-window address is the CTA's rank within the pair).
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint32_t dst, uint32_t bar, int col, int row) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "r"(col), "r"(row)
+      : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both] * B[smem halves of both]; issued by one thread of the leader CTA
+__device__ __forceinline__ void mma_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at this offset in both CTAs of the pair once the pair's MMAs issued so far have completed
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+// arrive on the mbarrier at this offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
