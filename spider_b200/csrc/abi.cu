@@ -1,4 +1,6 @@
 // libcsa_b200.so: ABI bookkeeping (version, errors, device checks, driver entry points).
+#include <cstdlib>
+
 #include "csa_internal.h"
 
 namespace csa {
@@ -42,6 +44,14 @@ uint32_t* debug_record_devptr() {
     }
   }
   return g_dbg_dev;
+}
+
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("CSA_PDL");
+    return !(e && atoi(e) == 0);
+  }();
+  return on;
 }
 
 int sm_count(int device) {

@@ -478,6 +478,9 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
+  // programmatic dependent launch: everything above overlapped the tail of the previous kernel of the stream
+  pdl_launch_dependents();
+  pdl_wait();
 
   // the softmax warpgroups keep a whole 128-column score row per thread: hand them the registers of warps 0-3
   // (setmaxnreg sits at the top of each role branch so that ptxas budgets every branch separately)
@@ -1106,8 +1109,19 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
       return set_error(static_cast<int>(ce), "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(ce));
     if (dev >= 0 && dev < 64) smem_set[dev][ki] = true;
   }
-  kern<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
-  ce = cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream_);
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  ce = cudaLaunchKernelEx(&cfg, kern, p);
+  if (ce == cudaSuccess) ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_error(static_cast<int>(ce), "csa_attn_kernel launch: %s", cudaGetErrorString(ce));
   return 0;
 }

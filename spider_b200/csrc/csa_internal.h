@@ -23,5 +23,7 @@ uint32_t* debug_record_devptr();
 
 // number of SMs if `device` is compute capability 10.x, else 0 (cached per device)
 int sm_count(int device);
+// programmatic dependent launch between the library's kernels (CSA_PDL=0 turns it off: A/B knob)
+bool pdl_enabled();
 
 }  // namespace csa

@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
   cluster_sync_all();    // the peer's barriers exist before anything of ours can reach them
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
+  // programmatic dependent launch: everything above overlapped the tail of the previous kernel of the stream
+  pdl_launch_dependents();
+  pdl_wait();
   const int n_items = p.pairs_m * p.tiles_n;
   const int kblocks = p.k / kGK;
 
@@ -366,11 +369,13 @@ static int gemm_launch(const csa_gemm_args_t* a, GemmParams& p, int dev, int sms
   const int ki = a->dtype == CSA_DTYPE_BF16 ? 1 : 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCl;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.blockDim = dim3(kGThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
@@ -394,6 +399,7 @@ static int gemm_launch(const csa_gemm_args_t* a, GemmParams& p, int dev, int sms
   const int cap = (dev >= 0 && dev < 64) ? max_clusters[dev][ki] : sms / kCl;
   const int clusters = n_items < cap ? n_items : cap;
   cfg.gridDim = dim3(static_cast<unsigned>(clusters * kCl), 1, 1);
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t ce = cudaLaunchKernelEx(&cfg, kern, p);
   if (ce != cudaSuccess) return set_error(static_cast<int>(ce), "csa_gemm_kernel launch: %s", cudaGetErrorString(ce));
   return 0;

@@ -162,6 +162,13 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
       "h"(cta_mask)
       : "memory");
 }
+// ---- programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start (prologue: barrier init, TMEM allocation, descriptor prefetch) while its predecessor in the stream drains;
+// it must not touch global memory before pdl_wait(), which returns once the predecessor has completed and flushed.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the successor be scheduled as SMs become free (it still waits for this grid's completion in its own pdl_wait)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- CTA pair (cta_group::2): two CTAs of a cluster, on the two SMs of a TPC, run ONE tcgen05.mma of M = 256: each
 // holds its own 128 rows of A and HALF of B's rows in shared memory, its own 128 rows of D in tensor memory; the
 // leader (cluster rank 0) issues.  All of these are executed as described per function.
