@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define CSA_ABI_VERSION 8
+#define CSA_ABI_VERSION 9
 
 #define CSA_E_BADARG (-1)   /* null pointer, non-positive size, misaligned pointer/stride */
 #define CSA_E_SHAPE (-2)    /* unsupported geometry (head_dim != 64, row stride not 16-byte aligned, ...) */
@@ -219,6 +219,14 @@ typedef struct csa_attn_args {
   int32_t _pad2;
   /* Optional: device uint32 added to ready_epoch on the device (see "Epochs in device memory" below); NULL = 0. */
   const uint32_t* epoch_base;
+  /* Optional (with `ready`): release the exchange buffers from INSIDE this launch — when its last CTA has finished,
+   * done_dst[r][peer_self] = ready_epoch (+ *epoch_base) is published on every GPU r != peer_self (st.release.sys),
+   * which is what csa_peer_signal does in a launch of its own.  done_dst[r]: GPU r's release flags (uint32[ready_n]),
+   * done_counter: LOCAL zero-initialised uint32 (left zero again).  done_counter == NULL: no release. */
+  uint32_t* done_dst[CSA_MAX_PEERS];
+  uint32_t* done_counter;
+  int32_t peer_self;
+  int32_t _pad3;
 } csa_attn_args_t;
 
 #define CSA_ATTN_NO_SPLIT 1 /* flags: process every unit whole even if a workspace is given */
@@ -345,6 +353,32 @@ int csa_linear(const csa_linear_args_t* args, void* stream);
  *     scatter_v[(g * scatter_dst_group_rows + pos) * scatter_ld + c - C]  = y[r][c]              c >= split_col
  * which replaces the separate csa_gather_kv launch and its second pass over K and V.
  */
+/*
+ * The fused gather AS THE MULTI-GPU EXCHANGE (csa_gemm_args_t.exchange): the epilogue stores every sampled row of this
+ * GPU's frames straight into the S-ordered K[S] / V[S] buffers of ALL GPUs of the CFG half over peer memory (NVLink;
+ * k_dst[self] is the local buffer) — projection, gather and exchange are one kernel, the transfer overlaps the main
+ * loop tile by tile — and the launch's last CTA publishes `epoch` to ready[r][self] on every GPU r, which is what
+ * csa_attn_fwd(ready = ...) there waits for.  Before its first remote store a CTA waits until done[r] >= done_epoch
+ * for every r != self (GPU r has finished the attention launch that last read the buffers being overwritten).  Same
+ * protocol, flags and epoch arithmetic as csa_peer_scatter_kv (below), which this replaces together with its re-read
+ * of K and V.  One group only: m == scatter_group_rows, destination row = scatter_pos[row].
+ */
+typedef struct csa_peer_exchange {
+  uint32_t struct_size; /* sizeof(csa_peer_exchange_t), checked */
+  int32_t n_peers;      /* 1 .. CSA_MAX_PEERS */
+  int32_t self;
+  int32_t _pad0;
+  void* k_dst[CSA_MAX_PEERS];
+  void* v_dst[CSA_MAX_PEERS];
+  int64_t dst_ld;                 /* elements */
+  uint32_t* ready[CSA_MAX_PEERS]; /* ready[r]: GPU r's arrival flags, uint32[n_peers] */
+  uint32_t epoch;
+  uint32_t done_epoch;
+  const uint32_t* done;       /* LOCAL uint32[n_peers], written by the peers */
+  uint32_t* counter;          /* LOCAL, zero (left zero again) */
+  const uint32_t* epoch_base; /* optional: epochs in device memory, see csa_peer_scatter_kv */
+} csa_peer_exchange_t;
+
 typedef struct csa_gemm_args {
   uint32_t struct_size; /* sizeof(csa_gemm_args_t), checked */
   int32_t dtype;        /* CSA_DTYPE_* of x, w, bias and y */
@@ -373,6 +407,9 @@ typedef struct csa_gemm_args {
   int64_t ldy2;
   int32_t y_split;
   int32_t _pad1;
+  /* Optional: the fused gather stores into the buffers of every GPU of the half (see csa_peer_exchange_t above);
+   * scatter_k / scatter_v / scatter_ld / scatter_dst_group_rows are then ignored.  NULL = local gather. */
+  const struct csa_peer_exchange* exchange;
 } csa_gemm_args_t;
 
 int csa_gemm(const csa_gemm_args_t* args, void* stream);

@@ -162,6 +162,10 @@ struct AttnKernelParams {
   int32_t ready_n;
   int32_t ready_bounds[CSA_MAX_PEERS + 1];
   int32_t ready_fpp;  // > 0: bounds come from `ranges` (frames per peer), not from ready_bounds
+  // optional: the launch's last CTA tells the peers that the exchange buffers of this epoch have been read
+  uint32_t* done_dst[CSA_MAX_PEERS];
+  uint32_t* done_counter;
+  int32_t peer_self;
   int32_t b_first;  // key order of a unit: contiguous B segment first, then the runs of A
 };
 
@@ -917,6 +921,19 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
+  if (p.done_counter != nullptr && threadIdx.x == 0) {
+    // every key tile this CTA fetched from the exchange buffers has been consumed (the grid-barrier idiom of peer.cu:
+    // CTA barrier above, one system-scope fence, the counter; the last CTA's release stores follow every increment)
+    __threadfence_system();
+    const uint32_t prev = atomicAdd(p.done_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *p.done_counter = 0u;
+      __threadfence_system();
+      const uint32_t epoch = p.ready_epoch + (p.epoch_base != nullptr ? *p.epoch_base : 0u);
+      for (int r = 0; r < p.ready_n; ++r)
+        if (r != p.peer_self) st_release_sys(p.done_dst[r] + p.peer_self, epoch);
+    }
+  }
 }
 
 
@@ -1044,6 +1061,19 @@ extern "C" int csa_attn_fwd(const csa_attn_args_t* a, void* stream_) {
     p.epoch_base = a->epoch_base;
     p.ready_n = a->ready_n;
     for (int r = 0; r <= a->ready_n; ++r) p.ready_bounds[r] = a->ready_bounds[r];
+    if (a->done_counter != nullptr) {
+      if (a->peer_self < 0 || a->peer_self >= a->ready_n || (reinterpret_cast<uintptr_t>(a->done_counter) & 3))
+        return set_error(CSA_E_BADARG, "csa_attn_fwd: peer_self %d outside [0, ready_n) or misaligned done_counter", a->peer_self);
+      for (int r = 0; r < a->ready_n; ++r) {
+        if (r != a->peer_self && !a->done_dst[r])
+          return set_error(CSA_E_BADARG, "csa_attn_fwd: null done_dst[%d]", r);
+        p.done_dst[r] = a->done_dst[r];
+      }
+      p.done_counter = a->done_counter;
+      p.peer_self = a->peer_self;
+    }
+  } else if (a->done_counter != nullptr) {
+    return set_error(CSA_E_BADARG, "csa_attn_fwd: done_counter needs ready flags");
   }
   p.dbg = debug_record_devptr();
 

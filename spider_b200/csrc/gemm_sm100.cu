@@ -80,6 +80,15 @@ struct GemmParams {
   int32_t scatter_group_rows, scatter_dst_group_rows, split_col;
   int32_t scatter_col0;  // columns below it are not gathered (the q part of a stacked q|k|v weight)
   uint32_t* dbg;
+  // the gather as the multi-GPU exchange (optional, n_dst > 0): sampled rows go to every GPU's K[S] / V[S]
+  int32_t n_dst, self;
+  uint16_t* k_dst[CSA_MAX_PEERS];
+  uint16_t* v_dst[CSA_MAX_PEERS];
+  uint32_t* ready[CSA_MAX_PEERS];
+  uint32_t epoch, done_epoch;
+  const uint32_t* done;
+  uint32_t* counter;
+  const uint32_t* epoch_base;
 };
 
 #define GSB(field) (sb + static_cast<uint32_t>(offsetof(Smem, field)))
@@ -202,6 +211,17 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     uint32_t fph[2] = {0, 0};
     int it = 0;
+    uint32_t epoch_base = 0;
+    if (p.n_dst > 0) {
+      // exchange: the buffers about to be overwritten were last read by the peers' attention launches of done_epoch
+      epoch_base = p.epoch_base != nullptr ? *p.epoch_base : 0u;
+      const int64_t done_epoch = p.epoch_base != nullptr
+                                     ? static_cast<int64_t>(epoch_base) + static_cast<int32_t>(p.done_epoch)
+                                     : static_cast<int64_t>(p.done_epoch);
+      if (lane < p.n_dst && lane != p.self && done_epoch > 0)
+        flag_wait_ge(p.done + lane, static_cast<uint32_t>(done_epoch), 0x540 + lane, p.dbg);
+      __syncwarp();
+    }
     for (int t = cluster_id; t < n_items; t += n_clusters, ++it) {
       const int buf = it & 1;
       const int m0 = ((t / p.tiles_n) * kCl + static_cast<int>(crank)) * kGM, n0 = (t % p.tiles_n) * kBN;
@@ -276,8 +296,8 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
         const int64_t yld = to_y2 ? p.ldy2 : p.ldy;
         const bool gather_cols = p.scatter_pos != nullptr && col0 >= p.scatter_col0;
         const bool is_v = col0 >= p.split_col;
-        uint16_t* sbase = reinterpret_cast<uint16_t*>(is_v ? p.scatter_v : p.scatter_k) +
-                          (col0 - (is_v ? p.split_col : p.scatter_col0));
+        const int scol = col0 - (is_v ? p.split_col : p.scatter_col0);
+        uint16_t* sbase = reinterpret_cast<uint16_t*>(is_v ? p.scatter_v : p.scatter_k) + scol;
         const int seg = lane & 7;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -292,8 +312,16 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
           const int rg = __shfl_sync(0xffffffffu, g, r);
           if (grow < p.m) {
             reinterpret_cast<uint4*>(ybase + static_cast<int64_t>(grow) * yld)[seg] = v4;
-            if (gather_cols && rpos >= 0)
-              reinterpret_cast<uint4*>(sbase + (static_cast<int64_t>(rg) * p.scatter_dst_group_rows + rpos) * p.scatter_ld)[seg] = v4;
+            if (gather_cols && rpos >= 0) {
+              if (p.n_dst == 0) {
+                reinterpret_cast<uint4*>(sbase + (static_cast<int64_t>(rg) * p.scatter_dst_group_rows + rpos) * p.scatter_ld)[seg] = v4;
+              } else {
+                const int64_t off = static_cast<int64_t>(rpos) * p.scatter_ld + scol;
+#pragma unroll
+                for (int r = 0; r < CSA_MAX_PEERS; ++r)
+                  if (r < p.n_dst) reinterpret_cast<uint4*>((is_v ? p.v_dst[r] : p.k_dst[r]) + off)[seg] = v4;
+              }
+            }
           }
         }
         __syncwarp();                                      // the staging rows are rewritten by the next 64 columns
@@ -303,6 +331,21 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) {
         if constexpr (k2Sm) mbar_arrive_cluster(GSB(acc_empty) + 8u * buf, 0); else mbar_arrive(GSB(acc_empty) + 8u * buf);
+      }
+    }
+    if (p.n_dst > 0) {
+      // publish (the grid-barrier idiom of peer.cu): the CTA's stores are ordered before one thread's system-scope
+      // fence by the barrier of its four epilogue warps, the fence before the counter, and the last CTA's flag stores
+      // come after every CTA's increment
+      named_bar_sync(1, 128);
+      if (warp == 2 && lane == 0) {
+        __threadfence_system();
+        const uint32_t prev = atomicAdd(p.counter, 1u);
+        if (prev == gridDim.x - 1) {
+          *p.counter = 0u;
+          __threadfence_system();
+          for (int r = 0; r < p.n_dst; ++r) st_relaxed_sys(p.ready[r] + p.self, epoch_base + p.epoch);
+        }
       }
     }
   }
@@ -439,7 +482,7 @@ extern "C" int csa_gemm(const csa_gemm_args_t* a, void* stream) {
   p.m = static_cast<int32_t>(a->m);
   p.n = static_cast<int32_t>(a->n);
   p.k = static_cast<int32_t>(a->k);
-  if (a->scatter_pos != nullptr) {
+  if (a->scatter_pos != nullptr && a->exchange == nullptr) {
     if (!a->scatter_k || !a->scatter_v || a->scatter_group_rows <= 0 || a->scatter_dst_group_rows <= 0 ||
         a->split_col <= 0 || (a->split_col % 32) || a->split_col > a->n || (a->scatter_ld & 7) ||
         a->scatter_col0 < 0 || (a->scatter_col0 % 32) || a->scatter_col0 > a->split_col ||
@@ -455,6 +498,43 @@ extern "C" int csa_gemm(const csa_gemm_args_t* a, void* stream) {
     p.scatter_dst_group_rows = a->scatter_dst_group_rows;
     p.split_col = a->split_col;
     p.scatter_col0 = a->scatter_col0;
+  }
+  if (a->exchange != nullptr) {
+    const csa_peer_exchange_t* x = a->exchange;
+    if (x->struct_size != sizeof(csa_peer_exchange_t))
+      return set_error(CSA_E_BADARG, "csa_gemm: exchange struct_size %u != %zu (ABI mismatch)", x->struct_size,
+                       sizeof(csa_peer_exchange_t));
+    if (a->scatter_pos == nullptr || a->scatter_group_rows <= 0 || a->m != a->scatter_group_rows || a->split_col <= 0 ||
+        (a->split_col % 32) || a->split_col > a->n || a->scatter_col0 < 0 || (a->scatter_col0 % 32) ||
+        a->scatter_col0 > a->split_col)
+      return set_error(CSA_E_BADARG, "csa_gemm: the exchange needs scatter_pos, one group (M == scatter_group_rows) and "
+                                     "scatter_col0 <= split_col, both multiples of 32");
+    if (x->n_peers < 1 || x->n_peers > CSA_MAX_PEERS || x->self < 0 || x->self >= x->n_peers || x->epoch == 0 ||
+        !x->done || !x->counter || (x->dst_ld & 7) || x->dst_ld < a->split_col - a->scatter_col0 ||
+        (x->epoch_base != nullptr && (reinterpret_cast<uintptr_t>(x->epoch_base) & 3)))
+      return set_error(CSA_E_BADARG, "csa_gemm: bad exchange (n_peers %d, self %d, epochs start at 1, dst_ld multiple "
+                                     "of 8 covering the columns)", x->n_peers, x->self);
+    p.scatter_pos = a->scatter_pos;
+    p.scatter_group_rows = a->scatter_group_rows;
+    p.scatter_dst_group_rows = 0;
+    p.split_col = a->split_col;
+    p.scatter_col0 = a->scatter_col0;
+    p.scatter_ld = x->dst_ld;
+    p.n_dst = x->n_peers;
+    p.self = x->self;
+    for (int r = 0; r < x->n_peers; ++r) {
+      if (!x->k_dst[r] || !x->v_dst[r] || !x->ready[r] ||
+          ((reinterpret_cast<uintptr_t>(x->k_dst[r]) | reinterpret_cast<uintptr_t>(x->v_dst[r])) & 15))
+        return set_error(CSA_E_BADARG, "csa_gemm: null or misaligned exchange buffer of peer %d", r);
+      p.k_dst[r] = static_cast<uint16_t*>(x->k_dst[r]);
+      p.v_dst[r] = static_cast<uint16_t*>(x->v_dst[r]);
+      p.ready[r] = x->ready[r];
+    }
+    p.epoch = x->epoch;
+    p.done_epoch = x->done_epoch;
+    p.done = x->done;
+    p.counter = x->counter;
+    p.epoch_base = x->epoch_base;
   }
   p.dbg = debug_record_devptr();
   int dev = 0;

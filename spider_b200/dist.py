@@ -145,6 +145,7 @@ class PeerExchange:
         self._ready = [f[0] for f in self.flags]
         self._done = [f[1] for f in self.flags]
         self._counter = self.flags[me][2]
+        self._counter2 = self.flags[me][2][1:]
         self.epoch = 0    # fresh flags: epochs restart
         self.allocations += 1
         dist.barrier(group=sh.half_group)          # every rank has mapped every buffer before the first store
@@ -189,6 +190,10 @@ class PeerExchange:
 
     def counter(self):
         return self._counter
+
+    def counter2(self):
+        """Second local counter (the attention launch's own release)."""
+        return self._counter2
 
 
 class ShardPlan:
@@ -235,6 +240,9 @@ class FrameSharding:
         # SMs the attention launch leaves to a CONCURRENT peer scatter on a side stream (0 = the scatter runs before
         # the attention launch on the same stream).  CSA_OVERLAP_SMS overrides (tuning).
         self.overlap_sms = int(os.environ.get("CSA_OVERLAP_SMS", "0"))
+        # p2p exchange fused into the K|V projection's epilogue and the release into the attention launch (three
+        # launches per layer instead of five); CSA_FUSED_EXCHANGE=0: separate csa_peer_scatter_kv / csa_peer_signal
+        self.fused_exchange = os.environ.get("CSA_FUSED_EXCHANGE", "1") != "0"
         self._side_streams = {}
         self.peers: Optional[PeerExchange] = None
         if not dist.is_initialized():
@@ -314,9 +322,41 @@ class FrameSharding:
             cm._shard_plan = p
         return p[1]
 
-    def attn_write(self, q, k, v, o, N, heads, cm, Fl):
+    def can_fuse_exchange(self, cm) -> bool:
+        """True when the K|V projection can deliver the sampled rows to the peers itself (``begin_exchange``)."""
+        return (self.gc > 1 and self.exchange == "p2p" and self.fused_exchange and self.overlap_sms == 0
+                and cm.shared_sample)
+
+    def begin_exchange(self, cm, N: int, C: int, dtype, device, Fl: int) -> dict:
+        """Open the exchange of one layer call BEFORE its K|V projection: returns what ``native.gemm`` needs to store
+        this rank's sampled rows into every peer's K[S] / V[S] buffer from its epilogue (``scatter`` positions of the
+        local rows, ``exchange`` dict) and what ``attn_write(..., exchanged=ctx)`` needs afterwards."""
+        if Fl != self.id_length:
+            raise ValueError(f"sharding was built for id_length {self.id_length}, processor has {Fl}")
+        fr = self.frames_local
+        me = self.rank_in_half
+        pl = self.plan(cm, device)
+        if self.peers is None:
+            self.peers = PeerExchange(self, device)
+        ex = self.peers
+        rows = Fl * N + native.CSA_TILE
+        ex.ensure(rows * C * torch.empty((), dtype=dtype).element_size())
+        ex.epoch += 1
+        epoch = ex.epoch
+        ks, vs = ex.views(epoch % ex.SLOTS, rows, C, dtype)
+        pos = cm.sample_positions(device)[self.f0 * N:(self.f0 + fr) * N]    # local row -> position in S (or -1)
+        sent = self._p2p_sent.setdefault(id(pl.cm), [pl, 0])
+        sent[0] = pl
+        sent[1] += (self.gc - 1) * 2 * C * torch.empty((), dtype=dtype).element_size()
+        return {"epoch": epoch, "ks": ks, "vs": vs, "rows": rows, "pos": pos, "plan": pl,
+                "exchange": {"k_dst": ks, "v_dst": vs, "ready": ex.ready(), "self": me, "epoch": epoch,
+                             "done": ex.done()[me], "done_epoch": epoch - ex.SLOTS, "counter": ex.counter(),
+                             "epoch_base": ex.epoch_base}}
+
+    def attn_write(self, q, k, v, o, N, heads, cm, Fl, exchanged: Optional[dict] = None):
         """Write-mode consistent attention of the local frames (``__call1__``, Comic_Generation.py:129-196 with
-        mask[:F*N,:F*N]) with the sampled rows of the other ranks' frames fetched over NVLink."""
+        mask[:F*N,:F*N]) with the sampled rows of the other ranks' frames fetched over NVLink.  ``exchanged``: the
+        context of ``begin_exchange`` when the K|V projection has already delivered this rank's rows."""
         if Fl != self.id_length:
             raise ValueError(f"sharding was built for id_length {self.id_length}, processor has {Fl}")
         fr = self.frames_local
@@ -326,6 +366,17 @@ class FrameSharding:
             raise ValueError("sharded consistent attention needs masks whose rows share one sample vector")
         C = q.shape[1]
         pl = self.plan(cm, q.device)
+        if exchanged is not None:
+            ex = self.peers
+            me = self.rank_in_half
+            epoch = exchanged["epoch"]
+            native.attn_fwd(q, o, heads=heads, n_groups=1, n_frames=fr, n_q=N,
+                            k_a=exchanged["ks"][me], v_a=exchanged["vs"][me], a_group_rows=exchanged["rows"],
+                            ranges=pl.ranges, range_base=self.f0, range_step=1, k_b=k, v_b=v, b_group_rows=fr * N,
+                            cb=(0, N, N), b_first=True, ready=ex.ready()[me], ready_epoch=epoch, ready_peers=self.gc,
+                            ready_frames_per_peer=fr, epoch_base=ex.epoch_base,
+                            done=ex.done(), done_counter=ex.counter2(), peer_self=me)
+            return o
         if self.gc > 1 and self.exchange == "p2p":
             return self._attn_write_p2p(q, k, v, o, N, heads, pl, Fl)
         if self.gc == 1:

@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CSA_B200_LIB: developer knob to load an experimental build of the same ABI (kernel tuning sweeps); default in-tree
 LIB_PATH = os.environ.get("CSA_B200_LIB") or os.path.join(_HERE, "libcsa_b200.so")
 
-CSA_ABI_VERSION = 8
+CSA_ABI_VERSION = 9
 CSA_DTYPE_F16 = 0
 CSA_DTYPE_BF16 = 1
 CSA_TILE = 128
@@ -117,6 +117,10 @@ class CsaAttnArgs(ctypes.Structure):
         ("ready_frames_per_peer", c_int32),
         ("_pad2", c_int32),
         ("epoch_base", c_void_p),
+        ("done_dst", c_void_p * CSA_MAX_PEERS),
+        ("done_counter", c_void_p),
+        ("peer_self", c_int32),
+        ("_pad3", c_int32),
     ]
 
 
@@ -170,6 +174,26 @@ class CsaLinearArgs(ctypes.Structure):
     ]
 
 
+class CsaPeerExchange(ctypes.Structure):
+    """Mirror of ``csa_peer_exchange_t``."""
+
+    _fields_ = [
+        ("struct_size", c_uint32),
+        ("n_peers", c_int32),
+        ("self_", c_int32),
+        ("_pad0", c_int32),
+        ("k_dst", c_void_p * CSA_MAX_PEERS),
+        ("v_dst", c_void_p * CSA_MAX_PEERS),
+        ("dst_ld", c_int64),
+        ("ready", c_void_p * CSA_MAX_PEERS),
+        ("epoch", c_uint32),
+        ("done_epoch", c_uint32),
+        ("done", c_void_p),
+        ("counter", c_void_p),
+        ("epoch_base", c_void_p),
+    ]
+
+
 class CsaGemmArgs(ctypes.Structure):
     """Mirror of ``csa_gemm_args_t``."""
 
@@ -200,6 +224,7 @@ class CsaGemmArgs(ctypes.Structure):
         ("ldy2", c_int64),
         ("y_split", c_int32),
         ("_pad1", c_int32),
+        ("exchange", c_void_p),
     ]
 
 
@@ -564,14 +589,17 @@ def gemm_supported(m: int, n: int, k: int) -> bool:
 
 
 def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-         alpha: float = 1.0, scatter=None, out2: Optional[torch.Tensor] = None):
+         alpha: float = 1.0, scatter=None, out2: Optional[torch.Tensor] = None, exchange: Optional[dict] = None):
     """``out[M, N] = alpha * x[M, K] @ w[N, K].T (+ bias)`` with the hand-written sm_100a GEMM (see csa_gemm), same
     layouts as ``linear``; batchable.  ``scatter = (pos, k_s, v_s, group_rows, dst_group_rows, split_col[, col0])``
     fuses the gather of the sampled key rows into the epilogue (w = [w_k; w_v], or [w_q; w_k; w_v] with ``col0 = C``):
     a row ``r`` with ``pos[r % group_rows] >= 0`` is also stored into ``k_s`` / ``v_s`` at row
     ``(r // group_rows) * dst_group_rows + pos``.  With ``out2`` the product is split by column: ``out`` takes the
     first ``out.shape[1]`` columns, ``out2`` the rest (q and K|V of a stacked-weight GEMM in two buffers); returns
-    ``(out, out2)`` then."""
+    ``(out, out2)`` then.  ``exchange`` (a dict with the arguments of ``peer_scatter_kv``: k_dst, v_dst, ready, self,
+    epoch, done, done_epoch, counter, epoch_base) turns the fused gather into the multi-GPU exchange: the sampled rows
+    go to every GPU's K[S] / V[S] buffer and the launch raises this GPU's arrival flag there (csa_peer_exchange_t);
+    ``scatter = (pos, None, None, group_rows, 0, split_col[, col0])`` then."""
     _require_cuda(x, w)
     ensure_device(x.device)
     if x.dim() != 2 or w.dim() != 2 or x.stride(1) != 1 or w.stride(1) != 1 or x.shape[1] != w.shape[1] or \
@@ -602,7 +630,37 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if out2 is not None:
         a.y2, a.ldy2, a.y_split = out2.data_ptr(), out2.stride(0), out.shape[1]
     a.alpha = alpha
-    if scatter is not None:
+    xch = None
+    if exchange is not None:
+        if scatter is None:
+            raise CsaNativeError("gemm: the exchange needs scatter = (pos, None, None, group_rows, 0, split_col[, col0])")
+        pos, _, _, group_rows, _, split_col = scatter[:6]
+        if pos.dtype != torch.int32 or not pos.is_contiguous() or pos.numel() < group_rows or m != group_rows:
+            raise CsaNativeError("gemm: exchange needs int32 positions for exactly the M rows of x (one group)")
+        k_dst, v_dst, ready = exchange["k_dst"], exchange["v_dst"], exchange["ready"]
+        npeer = len(k_dst)
+        if not (1 <= npeer <= CSA_MAX_PEERS) or len(v_dst) != npeer or len(ready) != npeer:
+            raise CsaNativeError(f"gemm: exchange takes 1..{CSA_MAX_PEERS} peers, one K, V and flag buffer each")
+        xch = CsaPeerExchange()
+        xch.struct_size = ctypes.sizeof(CsaPeerExchange)
+        xch.n_peers, xch.self_ = npeer, exchange["self"]
+        ld = None
+        for r in range(npeer):
+            kd, vd = k_dst[r], v_dst[r]
+            if kd.dim() != 2 or kd.stride(1) != 1 or kd.dtype != x.dtype or vd.shape != kd.shape or \
+                    vd.stride(0) != kd.stride(0) or (ld is not None and kd.stride(0) != ld):
+                raise CsaNativeError("gemm: exchange buffers must be 2-D, of x's dtype and one row stride")
+            ld = kd.stride(0)
+            xch.k_dst[r], xch.v_dst[r], xch.ready[r] = kd.data_ptr(), vd.data_ptr(), ready[r].data_ptr()
+        xch.dst_ld = ld
+        xch.epoch, xch.done_epoch = exchange["epoch"], exchange["done_epoch"] & 0xffffffff
+        xch.done, xch.counter = exchange["done"].data_ptr(), exchange["counter"].data_ptr()
+        if exchange.get("epoch_base") is not None:
+            xch.epoch_base = exchange["epoch_base"].data_ptr()
+        a.scatter_pos, a.scatter_group_rows, a.split_col = pos.data_ptr(), group_rows, split_col
+        a.scatter_col0 = scatter[6] if len(scatter) > 6 else 0
+        a.exchange = ctypes.addressof(xch)
+    elif scatter is not None:
         pos, k_s, v_s, group_rows, dst_group_rows, split_col = scatter[:6]
         a.scatter_col0 = scatter[6] if len(scatter) > 6 else 0
         if pos.dtype != torch.int32 or not pos.is_contiguous() or pos.numel() < group_rows or \
@@ -614,7 +672,7 @@ def gemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         a.scatter_dst_group_rows, a.split_col = dst_group_rows, split_col
     lib = load()
     _issue(CSA_CALL_GEMM, a, lambda st: lib.csa_gemm(ctypes.byref(a), st), "csa_gemm", _stream_ptr(x), x,
-           keep=(x, w, bias, out, out2, scatter))
+           keep=(x, w, bias, out, out2, scatter, xch, exchange))
     LAUNCHES["csa_gemm"] += 1
     return out if out2 is None else (out, out2)
 
@@ -779,8 +837,12 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
              max_ctas: int = 0, ranges: Optional[torch.Tensor] = None, range_base: int = 0,
              range_step: int = 0, split=True, b_first: bool = False, ready: Optional[torch.Tensor] = None,
              ready_epoch: int = 0, ready_bounds=None, ready_peers: int = 0,
-             ready_frames_per_peer: int = 0, epoch_base: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Launch csa_attn_fwd on the current stream.  All matrices are 2-D ``(rows, heads*64)`` with unit column stride."""
+             ready_frames_per_peer: int = 0, epoch_base: Optional[torch.Tensor] = None,
+             done=None, done_counter: Optional[torch.Tensor] = None, peer_self: int = 0) -> torch.Tensor:
+    """Launch csa_attn_fwd on the current stream.  All matrices are 2-D ``(rows, heads*64)`` with unit column stride.
+    ``done`` (list of the peers' release-flag tensors) + ``done_counter`` (local zero int32) + ``peer_self``: the
+    launch itself publishes ``ready_epoch`` to the peers when it has finished reading the exchange buffers (what
+    ``peer_signal`` does in a launch of its own)."""
     _require_cuda(q, o)
     ensure_device(q.device)
     for t in (q, o, k_a, v_a, k_b, v_b):
@@ -834,6 +896,12 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
         else:
             for i, b in enumerate(ready_bounds):
                 a.ready_bounds[i] = b
+        if done_counter is not None:
+            if done is None or len(done) != n:
+                raise CsaNativeError("attn_fwd: done must hold one release-flag tensor per peer")
+            for r, t in enumerate(done):
+                a.done_dst[r] = t.data_ptr()
+            a.done_counter, a.peer_self = done_counter.data_ptr(), peer_self
     stream = _stream_ptr(q)
     if split:
         ws = attn_workspace(q.device, stream)
@@ -843,7 +911,7 @@ def attn_fwd(q: torch.Tensor, o: torch.Tensor, *, heads: int, n_groups: int, n_f
             raise CsaNativeError("ranges must be a contiguous int32 tensor of shape (lists, 4)")
         a.ranges, a.range_base, a.range_step = ranges.data_ptr(), range_base, range_step
     lib = load()
-    keep = (q, o, k_a, v_a, k_b, v_b, idx, counts, ranges, ready, epoch_base)
+    keep = (q, o, k_a, v_a, k_b, v_b, idx, counts, ranges, ready, epoch_base, done, done_counter)
     direct = lambda st: lib.csa_attn_fwd(ctypes.byref(a), st)   # noqa: E731
     if ATTN_EVENTS is not None:
         # kernel time of the attention launches on the launching stream (bench.py's roofline line)

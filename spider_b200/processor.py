@@ -225,10 +225,10 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
             native.abort_batch()
             raise
 
-    def _proj(self, x, w, bias=None, out=None, scatter=None, kv=False):
+    def _proj(self, x, w, bias=None, out=None, scatter=None, kv=False, exchange=None):
         """One projection: the hand-written GEMM when the shape allows, else cuBLASLt (never with a fused gather)."""
         if self.native_gemm and (kv or self.gemm_qo) and native.gemm_supported(x.shape[0], w.shape[0], x.shape[1]):
-            return native.gemm(x, w, bias, out=out, scatter=scatter)
+            return native.gemm(x, w, bias, out=out, scatter=scatter, exchange=exchange)
         if scatter is not None:
             raise native.CsaNativeError("fused gather needs the hand-written GEMM (shape not supported)")
         return native.linear(x, w, bias, out=out)
@@ -339,7 +339,7 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
 
         o = torch.empty_like(q)
 
-        def project_kv(scatter=None):
+        def project_kv(scatter=None, exchange=None):
             # the q and K|V projections of the current input, deferred until the branch is known (native path only)
             if kv_job is None:
                 return
@@ -347,10 +347,10 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
             if (self.native_gemm and self.fused_qkv and self.gemm_qo and pl[5] is not None
                     and native.gemm_supported(x2.shape[0], 3 * C, C)):
                 sc = None if scatter is None else (scatter[0], scatter[1], scatter[2], scatter[3], scatter[4], 2 * C, C)
-                native.gemm(x2, pl[5], out=q_out, out2=kv_out, scatter=sc)
+                native.gemm(x2, pl[5], out=q_out, out2=kv_out, scatter=sc, exchange=exchange)
             else:
                 self._proj(x2, pl[1], out=q_out)
-                self._proj(x2, pl[2], out=kv_out, scatter=scatter, kv=True)
+                self._proj(x2, pl[2], out=kv_out, scatter=scatter, kv=True, exchange=exchange)
 
         branch = "early"
         if cur_step < 5:                                        # :94-96
@@ -381,6 +381,12 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                         k_s, v_s = self._ks_buffers(q.device, 2 * cap, C, q.dtype)
                         fused = (k_s, v_s, cap)
                         project_kv(scatter=(pos, k_s, v_s, Fl * N, cap, C))
+                    elif (kv_job is not None and self.fused_gather and self.native_gemm and self.dist is not None
+                          and self.dist.can_fuse_exchange(cm) and native.gemm_supported(B * N, 2 * C, C)):
+                        # multi-GPU: the same epilogue stores the sampled rows into EVERY peer's K[S] / V[S] over
+                        # NVLink and raises this rank's arrival flag there (no scatter launch, no signal launch)
+                        fused = self.dist.begin_exchange(cm, N, C, q.dtype, q.device, Fl)
+                        project_kv(scatter=(fused["pos"], None, None, B * N, 0, C), exchange=fused["exchange"])
                     else:
                         project_kv()
                     self._attn_write(q, k, v, o, N, heads, cm, fused)
@@ -434,7 +440,7 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
         rows of all identity frames of the same CFG half."""
         Fl = self.id_length
         if self.dist is not None:
-            return self.dist.attn_write(q, k, v, o, N, heads, cm, Fl)
+            return self.dist.attn_write(q, k, v, o, N, heads, cm, Fl, exchanged=fused)
         if self.kv_gather == "pre" and cm.shared_sample:
             # mask row f = S u block_f: gather K[S], V[S] once (HBM-bound), then frame f attends the two runs of that
             # buffer that lie outside its own block + its own block in place

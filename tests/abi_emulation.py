@@ -69,7 +69,7 @@ def attn_fwd(q, o, *, heads, n_groups, n_frames, n_q, k_a=None, v_a=None, a_grou
              b_group_rows=0, idx=None, counts=None, list_base=-1, list_step=0, g_adjust=0, ca=(0, 0, 0),
              cb=(0, 0, 0), scale=None, max_ctas=0, ranges=None, range_base=0, range_step=0, split=True,
              b_first=False, ready=None, ready_epoch=0, ready_bounds=None, ready_peers=0, ready_frames_per_peer=0,
-             epoch_base=None):
+             epoch_base=None, done=None, done_counter=None, peer_self=0):
     C = q.shape[1]
     if epoch_base is not None:
         ready_epoch += int(epoch_base[0])
@@ -103,7 +103,69 @@ def attn_fwd(q, o, *, heads, n_groups, n_frames, n_q, k_a=None, v_a=None, a_grou
             keys = [torch.arange(kk.shape[0], dtype=torch.int32)]
             out = rp.gathered_attention(q[qs].float()[None], kk[None], vv[None], keys, heads)[0]
             o[qs] = out.to(o.dtype)
+    if done_counter is not None:
+        # the launch's last CTA releases the exchange buffers of this epoch on every peer (csa_attn_args_t.done_dst)
+        assert ready is not None and int(done_counter[0]) == 0
+        for r in range(len(done)):
+            if r != peer_self:
+                done[r][peer_self] = ready_epoch
+        PEER_LOG.append(("release", ready_epoch))
     return o
+
+
+def gemm(x, w, bias=None, out=None, alpha=1.0, scatter=None, out2=None, exchange=None):
+    """csa_gemm: y = alpha * x w^T (+ bias), optional second output, optional fused gather — local (scatter buffers)
+    or as the multi-GPU exchange (csa_peer_exchange_t: every peer's K[S] / V[S], arrival flags, release wait)."""
+    m, n = x.shape[0], w.shape[0]
+    y = alpha * (x.float() @ w.float().t())
+    if bias is not None:
+        y = y + bias.float()
+    y = y.to(x.dtype)
+    if out2 is not None:
+        n1 = out.shape[1]
+        out.copy_(y[:, :n1])
+        out2.copy_(y[:, n1:])
+    else:
+        if out is None:
+            out = torch.empty((m, n), dtype=x.dtype)
+        out.copy_(y)
+    if scatter is not None:
+        pos, k_s, v_s, group_rows, dst_group_rows, split_col = scatter[:6]
+        col0 = scatter[6] if len(scatter) > 6 else 0
+        if exchange is not None:
+            epoch, done_epoch = exchange["epoch"], exchange["done_epoch"]
+            eb = exchange.get("epoch_base")
+            if eb is not None:
+                epoch += int(eb[0])
+                done_epoch += int(eb[0])
+            me = exchange["self"]
+            assert m == group_rows and int(exchange["counter"][0]) == 0
+            for r in range(len(exchange["k_dst"])):
+                if r != me and done_epoch > 0:
+                    _wait_ge(exchange["done"], r, done_epoch, "done")
+            sel = (pos[:m] >= 0).nonzero().flatten()
+            dst = pos[:m][sel].long()
+            for r in range(len(exchange["k_dst"])):
+                exchange["k_dst"][r][dst] = y[sel, col0:split_col]
+                exchange["v_dst"][r][dst] = y[sel, split_col:]
+            for r in range(len(exchange["k_dst"])):
+                exchange["ready"][r][me] = epoch
+            PEER_LOG.append(("exchange", epoch, int(sel.numel()), done_epoch))
+        else:
+            for g in range(m // group_rows):
+                pg = pos[:group_rows]
+                sel = (pg >= 0).nonzero().flatten()
+                dst = g * dst_group_rows + pg[sel].long()
+                k_s[dst] = y[g * group_rows + sel, col0:split_col]
+                v_s[dst] = y[g * group_rows + sel, split_col:]
+    return out if out2 is None else (out, out2)
+
+
+def sample_positions(s_idx, s_count, n_cols, out=None):
+    c = min(int(s_count[0]) if s_count.dim() else int(s_count), n_cols)
+    pos = torch.full((n_cols,), -1, dtype=torch.int32) if out is None else out.fill_(-1)
+    pos[s_idx[:c].long()] = torch.arange(c, dtype=torch.int32)
+    return pos
 
 
 def _wait_ge(flags, i, value, what, timeout=120.0):
@@ -163,7 +225,8 @@ def install(monkeypatch_or_none, native, processor_cls=None):
     """Replace the native entry points by the emulations (monkeypatch fixture, or plain setattr when None)."""
     pairs = dict(compact_rows=compact_rows, sample_ranges=sample_ranges, gather_rows=gather_rows,
                  gather_kv=gather_kv, attn_fwd=attn_fwd, peer_scatter_kv=peer_scatter_kv, peer_signal=peer_signal,
-                 enable_peer_access=enable_peer_access, epoch_advance=epoch_advance)
+                 enable_peer_access=enable_peer_access, epoch_advance=epoch_advance, gemm=gemm,
+                 sample_positions=sample_positions)
     for name, fn in pairs.items():
         if monkeypatch_or_none is None:
             setattr(native, name, fn)

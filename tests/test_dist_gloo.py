@@ -183,6 +183,94 @@ def test_sharded_write_pass_matches_single_process_and_oracle(world, exchange, m
     assert len(seen) == world
 
 
+def _worker_fused(rank, world, port, q):
+    """The fused exchange of the GPU path, driven at the dist layer (on a GPU the processor does exactly this around
+    its K|V projection): begin_exchange -> gemm(exchange=...) -> attn_write(exchanged=...), three steps of two layer
+    shapes, against the unsharded computation of the same inputs."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    mp.set_sharing_strategy("file_system")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from spider_b200.dist import FrameSharding
+
+        abi_emulation.install(None, native, None)
+        sh = FrameSharding(FL, None, torch.device("cpu"), exchange="p2p")
+        assert sh.fused_exchange
+        random.seed(11)
+        torch.manual_seed(5)
+        m1, m2 = spider_b200.cal_attn_mask_xl(FL + 1, FL, 0.5, 0.5, H, W, "cpu", torch.float32)
+        sh.sync_masks(m1, m2)
+        g = torch.Generator().manual_seed(123)
+        w_qkv = torch.randn((3 * C, C), generator=g) * 0.05
+        fr, f0 = sh.frames_local, sh.f0
+        worst = 0.0
+        for step in range(STEPS):
+            for cm, n in ((m1, 16), (m2, 64)):
+                x_full = torch.randn((2 * FL * n, C), generator=g)           # both halves, all frames
+                # ---- unsharded: project, gather, attend (the single-GPU fused path through the same emulation)
+                qf, kvf = torch.empty((2 * FL * n, C)), torch.empty((2 * FL * n, 2 * C))
+                cap = FL * n + native.CSA_TILE
+                k_s, v_s = torch.zeros((2 * cap, C)), torch.zeros((2 * cap, C))
+                pos = cm.sample_positions("cpu")
+                native.gemm(x_full, w_qkv, out=qf, out2=kvf, scatter=(pos, k_s, v_s, FL * n, cap, 2 * C, C))
+                s_idx, s_count, ranges = cm.sample_list("cpu")
+                want = torch.empty_like(qf)
+                native.attn_fwd(qf, want, heads=HEADS, n_groups=2, n_frames=FL, n_q=n, k_a=k_s, v_a=v_s,
+                                a_group_rows=cap, ranges=ranges, range_base=0, range_step=1, k_b=kvf[:, :C],
+                                v_b=kvf[:, C:], b_group_rows=FL * n, cb=(0, n, n))
+                # ---- sharded: this rank's frames of its half
+                r0 = (sh.cfg * FL + f0) * n
+                x = x_full[r0:r0 + fr * n].contiguous()
+                q_l, kv_l = torch.empty((fr * n, C)), torch.empty((fr * n, 2 * C))
+                assert sh.can_fuse_exchange(cm)
+                ctx = sh.begin_exchange(cm, n, C, torch.float32, torch.device("cpu"), FL)
+                native.gemm(x, w_qkv, out=q_l, out2=kv_l, scatter=(ctx["pos"], None, None, fr * n, 0, 2 * C, C),
+                            exchange=ctx["exchange"])
+                o = torch.empty_like(q_l)
+                sh.attn_write(q_l, kv_l[:, :C], kv_l[:, C:], o, n, HEADS, cm, FL, exchanged=ctx)
+                worst = max(worst, (o - want[r0:r0 + fr * n]).abs().max().item())
+            sh.end_step()
+            m1.resample_(0.5, torch.float32, post_sample=sh.sync_sample)
+            m2.resample_(0.5, torch.float32, post_sample=sh.sync_sample)
+        q.put((rank, worst, list(abi_emulation.PEER_LOG), (sh.peers.allocations, sh.peers.epoch)))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_fused_exchange_protocol(world):
+    """csa_gemm(exchange=...) + csa_attn_fwd(done_dst=...): the K|V projection delivers the sampled rows to every peer
+    and raises the arrival flags, the attention launch releases the buffers itself — no csa_peer_scatter_kv and no
+    csa_peer_signal launch (except the pad of an odd step), same epochs and slot discipline as the unfused path."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker_fused, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n_calls = STEPS * 2
+    for rank, worst, peer_log, peer_state in results:
+        assert worst < 2e-5, (rank, worst)
+        kinds = [e[0] for e in peer_log if e[0] != "advance"]
+        # the smaller layer comes first: the buffers are re-allocated by the second call, epochs restart there, and the
+        # (then odd) first step is padded with an epoch that is only released (PeerExchange.end_step)
+        assert kinds == ["exchange", "release", "exchange", "release", "signal"] + ["exchange", "release"] * (n_calls - 2)
+        assert "scatter" not in kinds
+        assert [e for e in peer_log if e[0] == "advance"] == [("advance", 2)] * STEPS
+        ex = [e for e in peer_log if e[0] == "exchange"]
+        assert [e[1] for e in ex] == [1, 1] + list(range(3, n_calls + 1))
+        assert all(e[3] == e[1] - 2 for e in ex)                       # slot reuse waits for epoch - 2
+        assert [e[1] for e in peer_log if e[0] == "release"] == [e[1] for e in ex]
+        assert peer_state == (2, 0)
+
+
 def _read_inputs(world):
     g = torch.Generator().manual_seed(77)
     return [[[torch.randn((2, n, C), generator=g) for n in (16, 64)] for _ in range(STEPS)] for _ in range(world)]

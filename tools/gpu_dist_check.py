@@ -138,6 +138,7 @@ def main():
     modes = [("p2p", False), ("nccl", False)] + ([("p2p", True)] if args.graph else [])
     kept = None
     for exchange, graph in modes:
+        scatter0 = native.LAUNCHES["csa_peer_scatter_kv"]
         outs, sh, host_s, procs_s = run(exchange, graph=graph, skew=args.skew)
         err = 0.0
         for got_step, ref_step in zip(outs, full):
@@ -146,7 +147,10 @@ def main():
                 err = max(err, (got - want).abs().max().item())
         worst[(exchange, graph)] = err
         if sh.gc > 1 and exchange == "p2p" and not graph:
-            assert sh.peers is not None and native.LAUNCHES["csa_peer_scatter_kv"] >= steps * len(layers)
+            assert sh.peers is not None
+            scatters = native.LAUNCHES["csa_peer_scatter_kv"] - scatter0
+            # fused exchange: the K|V projection delivers the rows itself — no scatter launch at all
+            assert scatters == (0 if sh.fused_exchange else steps * len(layers)), scatters
         if exchange == "p2p" and not graph:
             kept = (sh, host_s, procs_s)
     # ------------------------------------------------------------------ the story finishes: frame-parallel reads
