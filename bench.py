@@ -614,7 +614,7 @@ def run_b200_arm(args):
                                     "efficiency_vs_n1_ms": round(N1_F16_MS / ms4 / world, 4),
                                     "note": ("strong scaling of the 16-frame 1024^2 story (BASELINE config 4); "
                                              "efficiency = (N=1 ms measured by this repo on one B200, "
-                                             "profiles/r02_f16_n1.json) / (N x ms at N GPUs)")}
+                                             "profiles/r03_f16_n1.json) / (N x ms at N GPUs)")}
                 del wl4
             except Exception as e:   # noqa: BLE001
                 extra["config4"] = {"error": f"{type(e).__name__}: {e}"[:200]}
@@ -876,13 +876,15 @@ def hbm_kernels(args, wl, dev):
 
 
 def _n1_f16_ms() -> float:
-    """16-frame 1024^2 story on ONE B200, ms per denoise step: profiles/r02_f16_n1.json when this round re-measured
-    it (python bench.py --frames 16 --share-weights), else round 1's figure (profiles/r01d_scale)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r02_f16_n1.json")) as f:
-            return float(json.load(f)["ms_per_step"])
-    except (OSError, ValueError, KeyError):
-        return 158.0
+    """16-frame 1024^2 story on ONE B200, ms per denoise step, as last measured by this repo with the current kernels
+    (python bench.py --frames 16 --share-weights -> profiles/r03_f16_n1.json, else the earlier r02 file)."""
+    for name in ("r03_f16_n1.json", "r02_f16_n1.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.loads(f.read().strip().splitlines()[-1])["ms_per_step"])
+        except (OSError, ValueError, KeyError, IndexError):
+            continue
+    return 158.0
 
 
 N1_F16_MS = _n1_f16_ms()

@@ -340,10 +340,15 @@ typedef struct csa_linear_args {
 int csa_linear(const csa_linear_args_t* args, void* stream);
 
 /*
- * The same projections as a HAND-WRITTEN sm_100a GEMM (csrc/gemm_sm100.cu: TMA-fed 5-stage ring, tcgen05.mma M128 N128
- * K16 with two TMEM accumulators, epilogue in registers):  y = alpha * x w^T (+ bias), layouts as csa_linear.  Shapes of
+ * The same projections as a HAND-WRITTEN sm_100a GEMM (csrc/gemm_sm100.cu: persistent CTA pairs, TMA-fed ring of
+ * 4-8 stages, one tcgen05.mma.cta_group::2 of M256 N256 K16 per k step issued by the pair's leader — each CTA keeps its
+ * own 128 rows of x and half of the w tile — two TMEM accumulators per CTA, epilogue staged through shared memory so
+ * that stores cover whole 128-byte lines; N % 256 == 128 shapes that would waste more than 1/8 of the MMAs use
+ * 128-wide tiles with the w tile multicast instead):  y = alpha * x w^T (+ bias), layouts as csa_linear.  Shapes of
  * the path only: N % 128 == 0 and K % 64 == 0 (csa_gemm_supported); anything else stays with csa_linear.  With a
  * stacked weight [w_q; w_k; w_v] (n = 3C) ONE launch projects q, K and V of a layer: y = q, y2 = K|V (y_split = C).
+ * Launched with programmatic stream serialization (the prologue overlaps the previous kernel's tail; CSA_PDL=0 in
+ * the environment turns that off), like csa_attn_fwd.
  *
  * Fused K/V gather (optional, the write pass of the consistent branch, Comic_Generation.py:164-165 feeding :175-177):
  * when x holds `m / scatter_group_rows` groups (CFG halves) of key rows and w = [w_k; w_v] (n = 2C, split_col = C),
@@ -360,7 +365,7 @@ int csa_linear(const csa_linear_args_t* args, void* stream);
  * loop tile by tile — and the launch's last CTA publishes `epoch` to ready[r][self] on every GPU r, which is what
  * csa_attn_fwd(ready = ...) there waits for.  Before its first remote store a CTA waits until done[r] >= done_epoch
  * for every r != self (GPU r has finished the attention launch that last read the buffers being overwritten).  Same
- * protocol, flags and epoch arithmetic as csa_peer_scatter_kv (below), which this replaces together with its re-read
+ * protocol, flags and epoch arithmetic as csa_peer_scatter_kv (above), which this replaces together with its re-read
  * of K and V.  One group only: m == scatter_group_rows, destination row = scatter_pos[row].
  */
 typedef struct csa_peer_exchange {

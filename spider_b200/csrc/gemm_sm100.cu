@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
   using Smem = GemmSmem<kBN, k2Sm>;
   constexpr int kStages = GemmCfg<kBN, k2Sm>::kStages;
   constexpr int kTileB = GemmCfg<kBN, k2Sm>::kTileB;
+  constexpr int kAcc = kBN <= 128 ? 128 : 256;   // TMEM columns between the two accumulators
+  constexpr int kTmemCols = 2 * kAcc;            // a power of two
   extern __shared__ uint8_t smem_raw[];
   // the dynamic shared-memory window starts at the same offset in both CTAs of the cluster, so rounding it up gives
   // the same offsets too (multicast loads and commits address the peer by offset)
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
     fence_mbar_init();
   }
   if (warp == 1) {
-    if constexpr (k2Sm) tmem_alloc_2sm<2 * kBN>(GSB(tmem_base)); else tmem_alloc<2 * kBN>(GSB(tmem_base));
+    if constexpr (k2Sm) tmem_alloc_2sm<kTmemCols>(GSB(tmem_base)); else tmem_alloc<kTmemCols>(GSB(tmem_base));
   }
   tc_fence_before();
   __syncthreads();
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
         aph[buf] ^= 1;
       }
       tc_fence_after();
-      const uint32_t tacc = tmem + buf * kBN;
+      const uint32_t tacc = tmem + buf * kAcc;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(GSB(full) + 8u * st, ph, 0x520, p.dbg);
         tc_fence_after();
@@ -241,15 +243,17 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
       // (thread-per-row 16-byte stores cost 8x the L2 write transactions and ran the fused gather at 1.5 TB/s).
       const uint32_t stage_u32 = GSB(stage) + static_cast<uint32_t>(warp - 2) * kStageBytes;
 #pragma unroll 1
-      for (int cp = 0; cp < kBN / 64; ++cp) {
+      for (int cp = 0; cp < (kBN + 63) / 64; ++cp) {
         const int col0 = n0 + cp * 64;
         if (col0 >= p.n) break;                          // ragged last n tile (N % kBN != 0): nothing beyond N
+        const bool two = cp * 64 + 32 < kBN;             // false for the last 32 columns of a 160-wide tile
         uint32_t acc[2][32];
-        tmem_ld32(tmem + lane_base + buf * kBN + cp * 64, acc[0]);
-        tmem_ld32(tmem + lane_base + buf * kBN + cp * 64 + 32, acc[1]);
+        tmem_ld32(tmem + lane_base + buf * kAcc + cp * 64, acc[0]);
+        if (two) tmem_ld32(tmem + lane_base + buf * kAcc + cp * 64 + 32, acc[1]);
         tc_wait_ld();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+          if (h == 1 && !two) break;
           float bv[32];
           if (p.bias != nullptr) {
             const uint4* bp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias) + col0 + h * 32);
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
           const int grow = m0 + q * 32 + r;
           const int rpos = __shfl_sync(0xffffffffu, pos, r);
           const int rg = __shfl_sync(0xffffffffu, g, r);
-          if (grow < p.m) {
+          if (grow < p.m && (two || seg < 4)) {
             reinterpret_cast<uint4*>(ybase + static_cast<int64_t>(grow) * yld)[seg] = v4;
             if (gather_cols && rpos >= 0) {
               if (p.n_dst == 0) {
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
   cluster_sync_all();    // nobody leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    if constexpr (k2Sm) tmem_dealloc_2sm<2 * kBN>(tmem); else tmem_dealloc<2 * kBN>(tmem);
+    if constexpr (k2Sm) tmem_dealloc_2sm<kTmemCols>(tmem); else tmem_dealloc<kTmemCols>(tmem);
   }
 }
 
@@ -554,6 +558,26 @@ extern "C" int csa_gemm(const csa_gemm_args_t* a, void* stream) {
     const char* e = getenv("CSA_GEMM_2SM");
     return !(e && atoi(e) == 0);
   }();
+  // 160-wide tiles (pair MMA, N = 160) for plain projections whose N they divide when they need fewer tile-waves than
+  // the choice above: N = 1280 is 2.16 waves of 256-wide tiles at M = 8192 (three passes of 256 columns) but 3.46 of
+  // 160-wide ones (four passes of 160); N = 640 is four exact tiles instead of five 128-wide ones.  The model: passes
+  // x tile width, +5 % for the 160-wide tile's extra operand traffic per FLOP, +15 % for the 128-wide one's.
+  // OPT-IN (CSA_GEMM_BN160=1): timed alone the output projection of the 32x32 layer gains (29.4 -> 26.8 us, cuBLASLt
+  // 26.0), but inside the power-capped denoise step it LOSES (14.80 vs 14.72 ms per step, three alternating runs,
+  // profiles/r03h_gemm_bn160.log): 30 % more operand traffic per launch costs more than the shorter tail saves.
+  static const bool allow160 = []() {
+    const char* e = getenv("CSA_GEMM_BN160");
+    return e && atoi(e) == 1;
+  }();
+  if (allow160 && two_sm && a->y2 == nullptr && a->scatter_pos == nullptr && a->n % 160 == 0) {
+    const int64_t clusters = sms / 2;
+    const int64_t pairs = (blocks_m + 1) / 2;
+    auto passes = [&](int64_t tiles) { return (pairs * tiles + clusters - 1) / clusters; };
+    const double cost160 = static_cast<double>(passes(a->n / 160)) * 160 * 1.05;
+    const double cost_now = wide ? static_cast<double>(passes(tiles_wide)) * 256
+                                 : static_cast<double>(passes(a->n / 128)) * 128 * 1.15;
+    if (cost160 < cost_now * 0.97) return gemm_launch<160, true>(a, p, dev, sms, stream);
+  }
   if (wide) return two_sm ? gemm_launch<256, true>(a, p, dev, sms, stream) : gemm_launch<256, false>(a, p, dev, sms, stream);
   // 128-wide tiles stay on the multicast form: the pair MMA with N = 128 measured slower (41.6 vs 37.5 us on
   // 32768 x 640 x 640; CSA_GEMM_2SM=2 forces it)
