@@ -366,6 +366,13 @@ class FrameSharding:
             raise ValueError("sharded consistent attention needs masks whose rows share one sample vector")
         C = q.shape[1]
         pl = self.plan(cm, q.device)
+        if exchanged is not None and self.gc == 1:
+            # one CFG half per GPU and the K|V projection has already filled K[S] / V[S] from its epilogue
+            k_s, v_s, cap = exchanged
+            native.attn_fwd(q, o, heads=heads, n_groups=1, n_frames=fr, n_q=N,
+                            k_a=k_s, v_a=v_s, a_group_rows=cap, ranges=pl.ranges, range_base=self.f0, range_step=1,
+                            k_b=k, v_b=v, b_group_rows=fr * N, cb=(0, N, N))
+            return o
         if exchanged is not None:
             ex = self.peers
             me = self.rank_in_half

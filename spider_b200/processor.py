@@ -372,7 +372,8 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
                                          f"{'' if self.dist is None else f' sharded to {want_b} per rank'}, got {B} "
                                          "(the reference fails with a mask shape error here)")
                     fused = None
-                    if (kv_job is not None and self.fused_gather and self.native_gemm and self.dist is None
+                    local_only = self.dist is None or self.dist.gc == 1   # gc == 1: one whole CFG half per rank
+                    if (kv_job is not None and self.fused_gather and self.native_gemm and local_only
                             and self.kv_gather == "pre" and cm.shared_sample
                             and native.gemm_supported(B * N, 2 * C, C)):
                         # the K|V GEMM's epilogue stores the sampled rows into K[S] / V[S] (no gather launch)
