@@ -123,3 +123,77 @@ def test_fused_gather_equals_gather_kv(Fl, N, C):
         assert torch.equal(k_s[grp * cap:grp * cap + cnt], k_ref[grp * cap:grp * cap + cnt])
         assert torch.equal(v_s[grp * cap:grp * cap + cnt], v_ref[grp * cap:grp * cap + cnt])
         assert float((k_s[grp * cap + cnt:(grp + 1) * cap].float() - 7.0).abs().max()) == 0.0   # untouched
+
+
+@pytest.mark.parametrize("n_peers", [1, 2])
+def test_fused_exchange_on_one_gpu(n_peers):
+    """csa_gemm(exchange=...) and csa_attn_fwd(done_dst=...) with every "peer" buffer on this GPU (the kernels only
+    see pointers): the epilogue stores this rank's sampled rows into all destination buffers at their position in S
+    and raises its arrival flag in each, over several epochs with device-resident epoch arithmetic; the attention
+    launch waits for the flag, reproduces the single-GPU launch, and publishes the release flags itself."""
+    dtype = torch.bfloat16
+    Fl, N, C, heads = 4, 256, 128, 2
+    T = Fl + 1
+    me = n_peers - 1                       # this "rank" holds the last frames of the half
+    fr = Fl // n_peers
+    f0 = me * fr
+    g = torch.Generator(device=DEV).manual_seed(11)
+    sample = torch.rand((T * N,), device=DEV, generator=g) < 0.5
+    cm = csa_masks.CompactMask(T, Fl, N, sample=sample)
+    s_idx, s_count, ranges = cm.sample_list(DEV)
+    pos = cm.sample_positions(DEV)
+    rows = Fl * N + native.CSA_TILE
+    w_qkv = (torch.randn((3 * C, C), device=DEV, generator=g) * C ** -0.5).to(dtype)
+    flags = torch.zeros((n_peers, 3, native.CSA_MAX_PEERS), dtype=torch.int32, device=DEV)
+    ready = [flags[r, 0] for r in range(n_peers)]
+    done = [flags[r, 1] for r in range(n_peers)]
+    counter, counter2 = flags[me, 2], flags[me, 2][1:]
+    epoch_base = torch.full((1,), 40, dtype=torch.int32, device=DEV)
+    for epoch in (1, 2, 3):
+        x_full = torch.randn((Fl * N, C), device=DEV, generator=g).to(dtype)      # one CFG half, all frames
+        # single-GPU result: fused local gather + one attention launch
+        q1 = torch.empty((Fl * N, C), device=DEV, dtype=dtype)
+        kv1 = torch.empty((Fl * N, 2 * C), device=DEV, dtype=dtype)
+        k_s, v_s = (torch.zeros((rows, C), device=DEV, dtype=dtype) for _ in range(2))
+        native.gemm(x_full, w_qkv, out=q1, out2=kv1, scatter=(pos, k_s, v_s, Fl * N, rows, 2 * C, C))
+        want = native.attn_fwd(q1, torch.empty_like(q1), heads=heads, n_groups=1, n_frames=Fl, n_q=N, k_a=k_s,
+                               v_a=v_s, a_group_rows=rows, ranges=ranges, range_base=0, range_step=1,
+                               k_b=kv1[:, :C], v_b=kv1[:, C:], b_group_rows=Fl * N, cb=(0, N, N))
+        # "sharded": this rank projects its own frames and delivers their sampled rows to every destination; the
+        # other frames' rows are put there by hand (what the other ranks' launches would do) with their flags
+        ks = [torch.full((rows, C), 7.0, device=DEV, dtype=dtype) for _ in range(n_peers)]   # finite: masked keys
+        vs = [torch.full((rows, C), 7.0, device=DEV, dtype=dtype) for _ in range(n_peers)]   # still enter P V as 0 * v
+        lo = int(ranges[f0][1].item()) if f0 > 0 else 0       # S position of this rank's first sampled row
+        if f0 > 0:
+            for r in range(n_peers):
+                ks[r][:lo] = k_s[:lo]
+                vs[r][:lo] = v_s[:lo]
+                flags[r, 0, :me] = 40 + epoch
+        x = x_full[f0 * N:].contiguous()
+        q2 = torch.empty((fr * N, C), device=DEV, dtype=dtype)
+        kv2 = torch.empty((fr * N, 2 * C), device=DEV, dtype=dtype)
+        for r in range(n_peers):                               # the peers released the slot two epochs ago
+            if r != me:
+                done[me][r] = 40 + epoch - 2
+        torch.cuda.synchronize()
+        native.gemm(x, w_qkv, out=q2, out2=kv2, scatter=(pos[f0 * N:], None, None, fr * N, 0, 2 * C, C),
+                    exchange={"k_dst": ks, "v_dst": vs, "ready": ready, "self": me, "epoch": epoch, "done": done[me],
+                              "done_epoch": epoch - 2, "counter": counter, "epoch_base": epoch_base})
+        o = native.attn_fwd(q2, torch.empty_like(q2), heads=heads, n_groups=1, n_frames=fr, n_q=N, k_a=ks[me],
+                            v_a=vs[me], a_group_rows=rows, ranges=ranges, range_base=f0, range_step=1,
+                            k_b=kv2[:, :C], v_b=kv2[:, C:], b_group_rows=fr * N, cb=(0, N, N), b_first=True,
+                            ready=ready[me], ready_epoch=epoch, ready_peers=n_peers, ready_frames_per_peer=fr,
+                            epoch_base=epoch_base, done=done, done_counter=counter2, peer_self=me)
+        torch.cuda.synchronize()
+        cnt = int(s_count.item())
+        for r in range(n_peers):
+            assert torch.equal(ks[r][lo:cnt], k_s[lo:cnt]) and torch.equal(vs[r][lo:cnt], v_s[lo:cnt])
+            assert int(flags[r, 0, me]) == 40 + epoch                     # arrival flag raised everywhere
+        assert int(counter[0]) == 0
+        # same math; the key order (own block first) and the work decomposition differ: output rounding only
+        assert (o.float() - want[f0 * N:].float()).abs().max().item() <= 4e-3
+        for r in range(n_peers):
+            if r != me:
+                assert int(flags[r, 1, me]) == 40 + epoch                 # released by the attention launch
+        assert int(counter2[0]) == 0
+    assert native.debug_stuck() is None
