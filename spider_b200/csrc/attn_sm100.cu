@@ -124,6 +124,9 @@ struct __align__(1024) AttnSmem {
   uint64_t s_full[2], s_free[2], p_ready[2], o_done[2];
   uint32_t tmem_base;
   uint32_t merge_flag;  // split units: this CTA delivered the last piece and merges (written by one thread)
+  // per softmax warp: where the current unit's result goes {q_row0, head, Q pair, piece, split unit} — written at the
+  // unit's start, read in its epilogue, so that nothing of it lives in registers across the tile loop
+  int32_t epi[8][8];
 };
 
 struct AttnKernelParams {
@@ -608,6 +611,11 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
 
     if (lane == 0) mbar_arrive(bar_f);  // S is free before the first QK of the kernel
 
+#if CSA_PINGPONG
+#define EPI_SLOT (tok_out - 1)   // 0..7, from a value that is live across the tile loop anyway
+#else
+#define EPI_SLOT (warp - 4)
+#endif
     for (int u = blockIdx.x; u < p.n_sched; u += gridDim.x) {
       const Unit w = decode_unit(p, u);
       const int nt = w.nt;
@@ -622,6 +630,14 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
         }
         continue;
       }
+      if (lane == 0) {
+        sm.epi[EPI_SLOT][0] = w.q_row0;
+        sm.epi[EPI_SLOT][1] = w.h;
+        sm.epi[EPI_SLOT][2] = w.qp;
+        sm.epi[EPI_SLOT][3] = w.piece;
+        sm.epi[EPI_SLOT][4] = w.split_unit;
+      }
+      __syncwarp();
       float m = -INFINITY;  // running max, already multiplied by scale*log2(e)
       float l = 0.f;
       TileWalker walk;
@@ -773,36 +789,45 @@ __global__ void __launch_bounds__(kThreads, 1) csa_attn_kernel(const __grid_cons
       }
       TRACE(12);
       od += nt;
-      // Where the result goes is decoded again here instead of being carried through the tile loop: the loop runs
-      // at the register limit (a 128-key score row per thread), and anything live across it is spilled or
-      // rematerialised on the latency chain of every tile.
-      int u_epi = u;
-      asm volatile("" : "+r"(u_epi));
-      const Unit e = decode_unit(p, u_epi);
+      // Where the result goes was left in shared memory at the unit's start instead of being carried through the tile
+      // loop: the loop runs at the register limit (a 128-key score row per thread), and anything live across it is
+      // spilled or rematerialised on the latency chain of every tile.
+      struct { int q_row0, h, qp, piece, split_unit; } e;
+      e.q_row0 = sm.epi[EPI_SLOT][0];
+      e.h = sm.epi[EPI_SLOT][1];
+      e.qp = sm.epi[EPI_SLOT][2];
+      e.piece = sm.epi[EPI_SLOT][3];
+      e.split_unit = sm.epi[EPI_SLOT][4];
       const bool row_ok = e.qp * (2 * kBM) + s * kBM + row < p.n_q;
       uint4* optr = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.o) +
                                              static_cast<int64_t>(e.q_row0 + s * kBM + row) * p.o_ld + e.h * kHD);
+#if CSA_TRACE
+      asm volatile("" ::"l"(optr));
+      TRACE(13);
+#endif
       if (e.piece < 0) {
         // whole unit: normalise, store
         const float inv = 1.0f / l;
+        uint32_t ov[2][32];
+        tmem_ld32(tO, ov[0]);
+        tmem_ld32(tO + 32, ov[1]);   // both halves in flight, one round trip
+        tc_wait_ld();
+        if (row_ok) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t ov[32];
-          tmem_ld32(tO + c * 32, ov);
-          tc_wait_ld();
-          if (row_ok) {
+          for (int c = 0; c < 2; ++c) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               uint4 v4;
-              v4.x = pack2<kBF16>(__uint_as_float(ov[8 * i + 0]) * inv, __uint_as_float(ov[8 * i + 1]) * inv);
-              v4.y = pack2<kBF16>(__uint_as_float(ov[8 * i + 2]) * inv, __uint_as_float(ov[8 * i + 3]) * inv);
-              v4.z = pack2<kBF16>(__uint_as_float(ov[8 * i + 4]) * inv, __uint_as_float(ov[8 * i + 5]) * inv);
-              v4.w = pack2<kBF16>(__uint_as_float(ov[8 * i + 6]) * inv, __uint_as_float(ov[8 * i + 7]) * inv);
+              v4.x = pack2<kBF16>(__uint_as_float(ov[c][8 * i + 0]) * inv, __uint_as_float(ov[c][8 * i + 1]) * inv);
+              v4.y = pack2<kBF16>(__uint_as_float(ov[c][8 * i + 2]) * inv, __uint_as_float(ov[c][8 * i + 3]) * inv);
+              v4.z = pack2<kBF16>(__uint_as_float(ov[c][8 * i + 4]) * inv, __uint_as_float(ov[c][8 * i + 5]) * inv);
+              v4.w = pack2<kBF16>(__uint_as_float(ov[c][8 * i + 6]) * inv, __uint_as_float(ov[c][8 * i + 7]) * inv);
               optr[c * 4 + i] = v4;
             }
           }
         }
         tc_fence_before();
+        TRACE(14);
       } else {
         // piece of a split unit: leave the unnormalised partial (O, m, l) of this row in the workspace; the CTA
         // that delivers the last piece of the unit (arrival counter) merges all of them — nobody waits for anybody.

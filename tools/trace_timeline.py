@@ -19,7 +19,7 @@ from spider_b200 import native  # noqa: E402
 dev = torch.device("cuda:0")
 SLOTS, EVENTS = 4, 8192
 NAMES = {1: "top", 2: "s_full", 3: "S in regs", 4: "max", 5: "o_done/rescale", 6: "token", 7: "exp issued",
-         8: "p_ready", 10: "unit", 11: "epi wait", 12: "epi go", 20: "qk: top", 21: "qk: k_full", 22: "qk: s_free",
+         8: "p_ready", 10: "unit", 11: "epi wait", 12: "epi go", 13: "epi decoded", 14: "epi stored", 20: "qk: top", 21: "qk: k_full", 22: "qk: s_free",
          23: "pv: top", 24: "pv: v_full", 25: "pv: p_ready", 26: "pv: issued", 30: "o_done wait", 31: "o_done ok",
          **{40 + c: f"P round {c}" for c in range(8)}}
 
@@ -63,7 +63,7 @@ def main():
         for (a, ta), (b, tb) in zip(ev, ev[1:]):
             seg.setdefault((a, b), []).append(tb - ta)
         for (a, b), d in sorted(seg.items(), key=lambda kv: -sum(kv[1])):
-            if len(d) >= 8:
+            if len(d) >= 3:
                 print(f"   {str(NAMES.get(a, a)):>16s} -> {str(NAMES.get(b, b)):<16s} n={len(d):5d}  median {statistics.median(d):7.0f}"
                       f"  mean {statistics.mean(d):7.0f}  p90 {sorted(d)[int(0.9 * len(d))]:7.0f}")
         if sl < 2:
