@@ -348,27 +348,27 @@ def install_lowvram(host, replace_sampler: bool = True, bank_store: Optional[str
 
 # ---------------------------------------------------------------------------------------------------- persistence
 def save_single_character_weights(unet, character, description, filepath):
-    """Same on-disk format as the reference (:437-457): ``{description, character, attn_name: {step: [cpu tensors]}}``
-    with one ``(2, K_img, C)`` tensor of sampled hidden tokens per reference image — files are interchangeable with
-    the reference's.  Needs ``bank_store="hidden"`` entries (the default) or loaded lists."""
-    weights_to_save = {"description": description, "character": character}
-    for attn_name, proc in unet.attn_processors.items():
-        if isinstance(proc, SpatialAttnProcessorLowVram):
-            weights_to_save[attn_name] = {}
-            for step_key, entry in proc.id_bank[character].items():
-                weights_to_save[attn_name][step_key] = [t.cpu().clone() for t in entry]
-    torch.save(weights_to_save, filepath)
+    """Same on-disk format as the reference (:437-457): ``{description, character, <processor name>: {step: [cpu
+    tensors]}}`` with one ``(2, K_img, C)`` tensor of sampled hidden tokens per reference image — files are
+    interchangeable with the reference's (``tests/golden/lowvram_bank_bob.pt`` was written by the reference's own
+    function).  Needs ``bank_store="hidden"`` entries (the default) or loaded lists."""
+    blob = {"description": description, "character": character}
+    for name, proc in unet.attn_processors.items():
+        if not isinstance(proc, SpatialAttnProcessorLowVram):
+            continue
+        blob[name] = {step: [t.cpu().clone() for t in entry] for step, entry in proc.id_bank[character].items()}
+    torch.save(blob, filepath)
 
 
 def load_single_character_weights(unet, filepath):
     """Mirror of the reference loader (:460-479): fills ``id_bank[character]`` of every low-VRAM processor."""
-    weights_to_load = torch.load(filepath, map_location=torch.device("cpu"))
-    character = weights_to_load["character"]
+    blob = torch.load(filepath, map_location=torch.device("cpu"))
+    character = blob["character"]
     device = getattr(unet, "device", None)
-    for attn_name, proc in unet.attn_processors.items():
-        if isinstance(proc, SpatialAttnProcessorLowVram):
-            proc.id_bank[character] = {}
-            for step_key, tensors in weights_to_load[attn_name].items():
-                proc.id_bank[character][step_key] = SampledBankEntry.from_list(
-                    [t.to(device) if device is not None else t for t in tensors])
-    return character, weights_to_load["description"]
+    for name, proc in unet.attn_processors.items():
+        if not isinstance(proc, SpatialAttnProcessorLowVram):
+            continue
+        proc.id_bank[character] = {
+            step: SampledBankEntry.from_list([t.to(device) if device is not None else t for t in tensors])
+            for step, tensors in blob[name].items()}
+    return character, blob["description"]

@@ -1,6 +1,9 @@
 """Generate tests/golden/lowvram.npz by running the UNMODIFIED low-VRAM reference processor on CPU.
 
 Run in the dev container only (needs /root/reference):   python tests/golden/make_golden_lowvram.py
+                                                         python tests/golden/make_golden_lowvram.py --blob-only
+(--blob-only leaves lowvram.npz alone and writes lowvram_bank_bob.pt: the id_bank of character "[Bob]" after the same
+scenario, saved by the reference's OWN save_single_character_weights, :437-457, also executed verbatim.)
 
 The reference class lives in StoryDiffusion/gradio_app_sdxl_specific_id_low_vram.py:99-366, a gradio application whose
 module scope loads models and builds a UI — it cannot be imported.  The class definition is therefore taken VERBATIM
@@ -63,7 +66,17 @@ def load_reference_class():
     return ns, ns["SpatialAttnProcessor2_0"]
 
 
-def main():
+def load_reference_function(ns, name):
+    """Executes the top-level function `name` of the reference file, verbatim, in the namespace of the class."""
+    lines = open(REF_FILE).read().split("\n")
+    start = next(i for i, ln in enumerate(lines) if ln.startswith(f"def {name}("))
+    end = next(i for i in range(start + 1, len(lines)) if lines[i] and not lines[i][0].isspace()
+               and not lines[i].startswith("#"))
+    exec(compile("\n".join(lines[start:end]), REF_FILE, "exec"), ns)
+    return ns[name]
+
+
+def main(blob_only=False):
     ns, cls = load_reference_class()
     H = W = 96
     C, heads, Fl, steps = 64, 1, 3, 4
@@ -112,6 +125,13 @@ def main():
                             out[f"{tag}_s{step}_{name}_{f}"] = ix.numpy().astype(np.int32)
     finally:
         random.random = real_random
+    if blob_only:
+        import types
+        save = load_reference_function(ns, "save_single_character_weights")
+        unet = types.SimpleNamespace(attn_processors={f"layer{li}": p for li, p in enumerate(procs)})
+        save(unet, "[Bob]", "a man, wearing a black suit", os.path.join(OUT, "lowvram_bank_bob.pt"))
+        print("lowvram_bank_bob.pt written by the reference's save_single_character_weights")
+        return
     out["draws"] = np.array(draws, dtype=np.float64)
     # bank of layer 2 (/16-class): per character, per step, per image (2, K, C)
     for ch, key in (("[Bob]", "bob"), ("[Alice]", "alice")):
@@ -123,4 +143,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(blob_only="--blob-only" in sys.argv)

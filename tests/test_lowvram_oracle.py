@@ -54,3 +54,43 @@ def test_lowvram_sampler_shapes_and_rng():
     for i in range(4):
         assert torch.equal(a[i], torch.nonzero(m32[i], as_tuple=True)[0])
         assert torch.equal(b[i], torch.nonzero(m16[i], as_tuple=True)[0])
+
+
+def test_bank_file_written_by_the_reference_loads_and_our_file_equals_it(tmp_path):
+    """tests/golden/lowvram_bank_bob.pt was written by the reference's OWN save_single_character_weights
+    (gradio_app_sdxl_specific_id_low_vram.py:437-457, executed verbatim by make_golden_lowvram.py --blob-only) after the
+    golden story's write pass of "[Bob]".  The product loader must fill the processors' banks from it with exactly the
+    tensors the reference recorded, and the product saver must write the same file back (same keys, same tensors)."""
+    import os
+    import types
+
+    from spider_b200 import lowvram
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lowvram_bank_bob.pt")
+    z = np.load(os.path.join(os.path.dirname(path), "lowvram.npz"))
+    host = types.SimpleNamespace(attn_count=0, total_count=3, cur_step=0, id_length=3, total_length=4, write=False,
+                                 sa32=0.5, sa64=0.5, height=96, width=96, indices1024=None, indices4096=None,
+                                 cur_character=["[Bob]"], character_dict={}, character_index_dict={},
+                                 invert_character_index_dict={}, ref_indexs_dict={}, ref_totals=[])
+    cls = lowvram.make_lowvram_processor_class(host)
+    unet = types.SimpleNamespace(attn_processors={f"layer{li}": cls(id_length=3, device="cpu") for li in range(3)},
+                                 device=torch.device("cpu"))
+    ch, desc = lowvram.load_single_character_weights(unet, path)
+    assert (ch, desc) == ("[Bob]", "a man, wearing a black suit")
+    bank = unet.attn_processors["layer2"].id_bank["[Bob]"]
+    assert sorted(bank) == [0, 1, 2, 3]
+    for step in range(4):
+        assert len(bank[step]) == 3
+        for i, t in enumerate(bank[step]):
+            assert np.array_equal(t.numpy(), z[f"bank_bob_s{step}_i{i}"])
+    # and back: the product's file holds what the reference's file holds
+    out = os.path.join(tmp_path, "bob.pt")
+    lowvram.save_single_character_weights(unet, "[Bob]", "a man, wearing a black suit", out)
+    ours, theirs = torch.load(out, map_location="cpu"), torch.load(path, map_location="cpu")
+    assert sorted(ours) == sorted(theirs)
+    for name in (k for k in theirs if k.startswith("layer")):
+        assert sorted(ours[name]) == sorted(theirs[name])
+        for step in theirs[name]:
+            assert len(ours[name][step]) == len(theirs[name][step])
+            for a, b in zip(ours[name][step], theirs[name][step]):
+                assert torch.equal(a, b)
