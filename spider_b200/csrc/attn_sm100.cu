@@ -24,13 +24,17 @@
 // How many of every 16 element pairs take the polynomial exp2 (FMA/ALU pipes, ptx.cuh poly_exp2_fast_x2: clamp-free,
 // degree 2 for a bf16 P, degree 3 for an fp16 P) instead of MUFU.EX2.  ptxas paces a warp's exp loop at one MUFU
 // every 8 cycles and fills the gaps (decoded stall fields: 16.1 clk per pair with or without the polynomial), so the
-// gain is small: 4/16 -> 864 vs 853 TFLOP/s on the 64x64 layer, 6/16 and more lose (profiles/r02h_classic_poly_sweep
-// .log).  Round 2 also built and measured two reorganisations that were meant to lift the MUFU wall and did not:
-// 16 softmax warps with the keys of a tile split between two warps per row (issue-bound: 475 instructions per tile
-// and warp, profiles/experiments/r02_16warp_keysplit.patch) and a lazily updated reference point that takes the row
-// max off the latency chain (the exp phase grows by what the chain loses, profiles/experiments/r02_lazy_max.patch).
+// gain is small: timed alone (a burst at full clocks) 4/16 -> 864 vs 853 TFLOP/s on the 64x64 layer, 6/16 and more
+// lose (profiles/r02h_classic_poly_sweep.log).  Inside the denoise step the GPU runs at its POWER CAP (1.70-1.78 of
+// 1.965 GHz) and the extra FMA-pipe instructions cost more clock than they save MUFU time: 14.59-14.60 ms per step
+// with 0/16 against 14.67-14.78 with 4/16, 15.06 with 6/16 (profiles/r03l_poly_in_step.log) — hence the default 0;
+// -DCSA_POLY_PAIRS=4 is the burst-optimal build.  Round 2 also built and measured two reorganisations that were meant
+// to lift the MUFU wall and did not: 16 softmax warps with the keys of a tile split between two warps per row
+// (issue-bound: 475 instructions per tile and warp, profiles/experiments/r02_16warp_keysplit.patch) and a lazily
+// updated reference point that takes the row max off the latency chain (the exp phase grows by what the chain loses,
+// profiles/experiments/r02_lazy_max.patch).
 #ifndef CSA_POLY_PAIRS
-#define CSA_POLY_PAIRS 4
+#define CSA_POLY_PAIRS 0
 #endif
 // Exp-phase ping-pong: the two softmax warps that share an SM sub-partition (same TMEM lane quarter, Q tile 0 and
 // Q tile 1) hand a token back and forth through a pair of named barriers, so that one exponentiates (MUFU-bound)
