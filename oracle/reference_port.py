@@ -248,3 +248,40 @@ def setup_seed(seed: int) -> None:
     torch.manual_seed(seed)
     np.random.seed(seed)
     random.seed(seed)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the stock processor of every other attention layer
+# ----------------------------------------------------------------------------------------------------------------
+def stock_attention(attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
+                    temb=None) -> torch.Tensor:
+    """``AttnProcessor2_0.__call__`` of StoryDiffusion/utils/gradio_utils.py:400-464 with ``attention_mask=None``
+    (what SDXL passes): optional spatial / group norm (:410-411, :429-430), 4-D input folded to tokens (:415-417),
+    q from the hidden states and K/V from the encoder states — the hidden states themselves for self-attention,
+    optionally normed for cross-attention (:432-440) —, per-head softmax(q k^T / sqrt(d)) v (:444-446), output
+    projection + dropout (:452-454), un-folding, residual and rescale (:456-462).  fp32.  Pinned to the unmodified
+    reference class by tests/golden/stock.npz (tests/golden/make_golden_stock.py)."""
+    residual = hidden_states
+    if attn.spatial_norm is not None:
+        hidden_states = attn.spatial_norm(hidden_states, temb)
+    ndim = hidden_states.ndim
+    if ndim == 4:
+        b, c, h, w = hidden_states.shape
+        hidden_states = hidden_states.view(b, c, h * w).transpose(1, 2)
+    if attn.group_norm is not None:
+        hidden_states = attn.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+    enc = hidden_states if encoder_hidden_states is None else encoder_hidden_states
+    if encoder_hidden_states is not None and attn.norm_cross:
+        enc = attn.norm_encoder_hidden_states(enc)
+    q = _project_heads(attn.to_q(hidden_states).float(), attn.heads)
+    k = _project_heads(attn.to_k(enc).float(), attn.heads)
+    v = _project_heads(attn.to_v(enc).float(), attn.heads)
+    o = F.scaled_dot_product_attention(q, k, v)
+    B, _, N, d = o.shape
+    o = o.transpose(1, 2).reshape(B, N, attn.heads * d)
+    out = attn.to_out[1](attn.to_out[0](o))
+    if ndim == 4:
+        out = out.transpose(-1, -2).reshape(b, c, h, w)
+    if attn.residual_connection:
+        out = out + residual
+    return out / attn.rescale_output_factor

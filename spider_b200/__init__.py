@@ -9,6 +9,7 @@ from .install import install, make_processor_class, set_attention_processor, uni
 from .graph import StepGraph  # noqa: E402,F401
 from .masks import CompactMask, cal_attn_mask_xl  # noqa: E402,F401
 from .processor import GLOBALS, SpatialAttnProcessor2_0, StoryGlobals  # noqa: E402,F401
+from .stock import AttnProcessor2_0  # noqa: E402,F401
 from .lowvram import (CompactIndices, SpatialAttnProcessorLowVram, cal_attn_indice_xl_effcient_memory,  # noqa: E402,F401
                       install_lowvram, load_single_character_weights, make_lowvram_processor_class,
                       save_single_character_weights)

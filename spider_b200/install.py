@@ -20,6 +20,7 @@ from typing import Optional
 
 from . import masks as _masks
 from .processor import GLOBALS, SpatialAttnProcessor2_0
+from .stock import AttnProcessor2_0
 
 _CONTROL_DEFAULTS = dict(write=False, cur_step=0, attn_count=0, total_count=0, sa32=0.5, sa64=0.5, height=768,
                          width=768, mask1024=None, mask4096=None)
@@ -36,8 +37,10 @@ def make_processor_class(host, bank_store: Optional[str] = None, validate_masks:
 
 
 def install(host, replace_mask_sampler: bool = True, bank_store: Optional[str] = None,
-            validate_masks: Optional[bool] = None):
-    """Rebind ``host.SpatialAttnProcessor2_0`` (and ``host.cal_attn_mask_xl``) to the B200 implementations.
+            validate_masks: Optional[bool] = None, replace_stock_processor: bool = True):
+    """Rebind ``host.SpatialAttnProcessor2_0`` (and ``host.cal_attn_mask_xl``, and ``host.AttnProcessor`` — the name
+    under which the reference instantiates its stock SDPA processor for every other attention layer,
+    Comic_Generation.py:17,368) to the B200 implementations.
 
     Returns the bound processor class.  Missing control globals are created with the reference's defaults so the
     host namespace is complete even before the driver sets them (:327-349).
@@ -53,10 +56,19 @@ def install(host, replace_mask_sampler: bool = True, bank_store: Optional[str] =
         if hasattr(host, "cal_attn_mask_xl") and not hasattr(host, "_csa_original_mask_sampler"):
             host._csa_original_mask_sampler = host.cal_attn_mask_xl
         host.cal_attn_mask_xl = _masks.cal_attn_mask_xl
+    if replace_stock_processor:
+        if hasattr(host, "AttnProcessor") and not hasattr(host, "_csa_original_stock_processor"):
+            host._csa_original_stock_processor = host.AttnProcessor
+        host.AttnProcessor = AttnProcessor2_0
     return cls
 
 
 def uninstall(host) -> None:
+    if hasattr(host, "_csa_original_stock_processor"):
+        host.AttnProcessor = host._csa_original_stock_processor
+        del host._csa_original_stock_processor
+    elif getattr(host, "AttnProcessor", None) is AttnProcessor2_0:
+        del host.AttnProcessor
     if hasattr(host, "_csa_original_processor"):
         host.SpatialAttnProcessor2_0 = host._csa_original_processor
         del host._csa_original_processor
@@ -69,8 +81,9 @@ def set_attention_processor(unet, id_length: int, host=GLOBALS, all_self_attn: b
                             other_processor=None, processor_cls=None) -> int:
     """Install processors on ``unet`` the way the reference does (Comic_Generation.py:270-290, :353-371):
     ``up_blocks.*.attn1`` (or every ``attn1`` with ``all_self_attn``) get the consistent-self-attention processor,
-    everything else keeps ``other_processor`` (default: whatever is installed).  Sets ``host.total_count`` to the
-    number of consistent processors and returns it."""
+    everything else ``other_processor`` — an instance, or ``"b200"`` for a fresh ``spider_b200.AttnProcessor2_0`` per
+    layer (the reference's ``AttnProcessor()``, :368, on the same kernels); default: whatever is installed.  Sets
+    ``host.total_count`` to the number of consistent processors and returns it."""
     cls = processor_cls
     if cls is None:
         installed = getattr(host, "SpatialAttnProcessor2_0", None)
@@ -87,7 +100,10 @@ def set_attention_processor(unet, id_length: int, host=GLOBALS, all_self_attn: b
             procs[name] = cls(id_length=id_length)
             count += 1
         else:
-            procs[name] = other_processor if other_processor is not None else current[name]
+            if isinstance(other_processor, str) and other_processor == "b200":
+                procs[name] = AttnProcessor2_0()
+            else:
+                procs[name] = other_processor if other_processor is not None else current[name]
     unet.set_attn_processor(copy.deepcopy(procs))   # the reference deep-copies the dict (:371)
     host.total_count = count
     return count
