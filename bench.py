@@ -679,8 +679,12 @@ def run_b200_arm(args):
             if e2e.get("link"):
                 lk = e2e["link"]
                 line["e2e"]["link"] = lk
-                line["e2e"]["link_floor_ms_per_step"] = round(
-                    max(e2e["h2d"], e2e["d2h"]) / (lk["both_GBps_per_direction"] * 1e9) * 1e3, 3)
+                # floor = this rank's bytes over what it gets of the host link: alone at N=1, its share of the box's
+                # total when all ranks copy at once
+                rate = lk["both_GBps_per_direction"]
+                if "all_ranks_at_once_GBps_per_direction_total" in lk:
+                    rate = lk["all_ranks_at_once_GBps_per_direction_total"] / world
+                line["e2e"]["link_floor_ms_per_step"] = round(max(e2e["h2d"], e2e["d2h"]) / (rate * 1e9) * 1e3, 3)
         if world == 1 and not args.no_cpu:
             base = cpu_reference_sample(args, steps=3, warmup=1, whole_step=False)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample")}
@@ -788,13 +792,22 @@ def run_e2e(args, wl, dev, barrier, rank):
             graph.replay() if graph is not None else e2e_step()
         e1.record()
         barrier()
+        # rank 0 alone (the others wait at the barrier), then every rank at once: the box's host link is shared
         link = measure_link(host_in, host_out, dev, s_in, s_out) if rank == 0 else None
+        barrier()
+        if args.gpus > 1:
+            mine = measure_link(host_in, host_out, dev, s_in, s_out, only_both=True, sync=barrier)
+            total = torch.tensor([mine], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(total)
+            if link is not None:
+                link["all_ranks_at_once_GBps_per_direction_total"] = round(float(total.item()), 1)
     return {"ms": e0.elapsed_time(e1), "h2d": h2d, "d2h": d2h, "mode": mode, "link": link}
 
 
-def measure_link(host_in, host_out, dev, s_in, s_out):
+def measure_link(host_in, host_out, dev, s_in, s_out, only_both=False, sync=None):
     """What the host link gives on this box with the e2e leg's own pinned buffers and nothing else running: H2D alone,
-    D2H alone, both at once (GB/s per direction) — the floor of the e2e step is bytes / the concurrent rate."""
+    D2H alone, both at once (GB/s per direction) — the floor of the e2e step is bytes / the concurrent rate.
+    ``only_both`` + ``sync`` (a barrier): this rank's both-directions rate while every other rank does the same."""
     dst = [torch.empty(x.shape, device=dev, dtype=x.dtype) for x in host_in[:8]]
     nbytes = sum(x.numel() * x.element_size() for x in host_in[:8])
 
@@ -820,6 +833,9 @@ def measure_link(host_in, host_out, dev, s_in, s_out):
         return 3 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
 
     run(True, True)
+    if only_both:
+        sync()
+        return run(True, True)
     return {"h2d_alone_GBps": round(run(True, False), 1), "d2h_alone_GBps": round(run(False, True), 1),
             "both_GBps_per_direction": round(run(True, True), 1)}
 
