@@ -72,6 +72,11 @@ struct GemmParams {
   float alpha;
   int32_t m, n, k;
   int32_t pairs_m, tiles_n;     // work items: (pair of vertically adjacent 128-row blocks, n tile)
+  // Tail halving (256-wide pair-MMA kernel): the items of the last, partial wave are cut in two along n — work items
+  // [n_whole, n_whole + 2 * n_halved) are halves (128 columns) of items [n_whole, n_whole + n_halved): the wave that
+  // would keep only a part of the clusters busy for a whole tile time takes half of it
+  int32_t n_whole, n_halved;
+  CUtensorMap tm_w_half;        // w with a box of kBN / 4 rows (a CTA's half of a 128-wide tile)
   // fused gather of the sampled rows (optional)
   const int32_t* scatter_pos;   // [scatter_group_rows]: position of a row in S, or -1
   void* scatter_k;              // K[S]: rows g * scatter_dst_group_rows + pos, columns [0, split_col)
@@ -92,6 +97,21 @@ struct GemmParams {
 };
 
 #define GSB(field) (sb + static_cast<uint32_t>(offsetof(Smem, field)))
+
+// work item t -> item (pair of m blocks x n tile), first column and width of its share of the tile
+template <int kBN>
+__device__ __forceinline__ void gemm_work(const GemmParams& p, int t, int& item, int& n0, int& width) {
+  if (t < p.n_whole) {
+    item = t;
+    n0 = (t % p.tiles_n) * kBN;
+    width = kBN;
+  } else {
+    const int h = t - p.n_whole;
+    item = p.n_whole + (h >> 1);
+    n0 = (item % p.tiles_n) * kBN + (h & 1) * (kBN / 2);
+    width = kBN / 2;
+  }
+}
 
 template <bool kBF16, int kBN, bool k2Sm>
 __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -139,7 +159,7 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
   // programmatic dependent launch: everything above overlapped the tail of the previous kernel of the stream
   pdl_launch_dependents();
   pdl_wait();
-  const int n_items = p.pairs_m * p.tiles_n;
+  const int n_items = p.n_whole + 2 * p.n_halved;   // work items (== pairs_m * tiles_n when nothing is halved)
   const int kblocks = p.k / kGK;
 
   if (warp == 0) {
@@ -148,16 +168,19 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
       int st = 0;
       uint32_t ph = 0;
       for (int t = cluster_id; t < n_items; t += n_clusters) {
-        const int m0 = ((t / p.tiles_n) * kCl + static_cast<int>(crank)) * kGM, n0 = (t % p.tiles_n) * kBN;
+        int item, n0, width;
+        gemm_work<kBN>(p, t, item, n0, width);
+        const int m0 = ((item / p.tiles_n) * kCl + static_cast<int>(crank)) * kGM;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(GSB(empty) + 8u * st, ph ^ 1, 0x500, p.dbg);
           if constexpr (k2Sm) {
             // both CTAs' tiles are credited to the leader's barrier: its MMA consumes both
-            if (crank == 0) mbar_arrive_expect_tx(GSB(full) + 8u * st, 2 * (kGTileA + kTileB));
+            const bool half = width < kBN;
+            if (crank == 0) mbar_arrive_expect_tx(GSB(full) + 8u * st, 2 * (kGTileA + (half ? kTileB / 2 : kTileB)));
             tma_load_2d_2sm(&p.tm_x, GSB(a) + static_cast<uint32_t>(kGTileA) * st, GSB(full) + 8u * st, kb * kGK, m0);
             // my half of the w tile's rows stays here
-            tma_load_2d_2sm(&p.tm_w, GSB(b) + static_cast<uint32_t>(kTileB) * st, GSB(full) + 8u * st, kb * kGK,
-                            n0 + static_cast<int>(crank) * (kBN / 2));
+            tma_load_2d_2sm(half ? &p.tm_w_half : &p.tm_w, GSB(b) + static_cast<uint32_t>(kTileB) * st,
+                            GSB(full) + 8u * st, kb * kGK, n0 + static_cast<int>(crank) * (width / 2));
           } else {
             mbar_arrive_expect_tx(GSB(full) + 8u * st, kGTileA + kTileB);   // x tile + every slice of the w tile
             tma_load_2d(&p.tm_x, GSB(a) + static_cast<uint32_t>(kGTileA) * st, GSB(full) + 8u * st, kb * kGK, m0);
@@ -172,6 +195,7 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
   } else if (warp == 1) {
     // ================================================================================================ MMA issue
     constexpr uint32_t idesc = make_idesc(k2Sm ? 2 * kGM : kGM, kBN, kBF16 ? 1 : 0, 0, 0);
+    constexpr uint32_t idesc_half = make_idesc(k2Sm ? 2 * kGM : kGM, kBN / 2, kBF16 ? 1 : 0, 0, 0);
     int st = 0;
     uint32_t ph = 0, aph[2] = {0, 0};
     int it = 0;
@@ -184,6 +208,7 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
       }
       tc_fence_after();
       const uint32_t tacc = tmem + buf * kAcc;
+      const uint32_t idesc_t = (k2Sm && t >= p.n_whole) ? idesc_half : idesc;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(GSB(full) + 8u * st, ph, 0x520, p.dbg);
         tc_fence_after();
@@ -192,7 +217,7 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
         if (elect_one()) {
           if constexpr (k2Sm) {
 #pragma unroll
-            for (int kk = 0; kk < kGK / 16; ++kk) mma_ss_2sm(tacc, da + kk * 2, db + kk * 2, idesc, (kb | kk) ? 1u : 0u);
+            for (int kk = 0; kk < kGK / 16; ++kk) mma_ss_2sm(tacc, da + kk * 2, db + kk * 2, idesc_t, (kb | kk) ? 1u : 0u);
             tc_commit_2sm(GSB(empty) + 8u * st);                        // free the stage in both CTAs
             if (kb == kblocks - 1) tc_commit_2sm(GSB(acc_full) + 8u * buf);  // both CTAs' epilogues
           } else {
@@ -226,7 +251,9 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
     }
     for (int t = cluster_id; t < n_items; t += n_clusters, ++it) {
       const int buf = it & 1;
-      const int m0 = ((t / p.tiles_n) * kCl + static_cast<int>(crank)) * kGM, n0 = (t % p.tiles_n) * kBN;
+      int item, n0, width;
+      gemm_work<kBN>(p, t, item, n0, width);
+      const int m0 = ((item / p.tiles_n) * kCl + static_cast<int>(crank)) * kGM;
       const int row = m0 + row_in_tile;
       const bool row_ok = row < p.m;
       mbar_wait(GSB(acc_full) + 8u * buf, fph[buf], 0x530 + buf, p.dbg);
@@ -245,7 +272,7 @@ __global__ void __launch_bounds__(kGThreads, 1) csa_gemm_kernel(const __grid_con
 #pragma unroll 1
       for (int cp = 0; cp < (kBN + 63) / 64; ++cp) {
         const int col0 = n0 + cp * 64;
-        if (col0 >= p.n) break;                          // ragged last n tile (N % kBN != 0): nothing beyond N
+        if (col0 >= p.n || cp * 64 >= width) break;      // ragged last n tile (N % kBN != 0) / a halved tail item
         const bool two = cp * 64 + 32 < kBN;             // false for the last 32 columns of a 160-wide tile
         uint32_t acc[2][32];
         tmem_ld32(tmem + lane_base + buf * kAcc + cp * 64, acc[0]);
@@ -409,6 +436,8 @@ static int gemm_launch(const csa_gemm_args_t* a, GemmParams& p, int dev, int sms
   p.pairs_m = static_cast<int32_t>((a->m + kCl * kGM - 1) / (kCl * kGM));
   p.tiles_n = static_cast<int32_t>((a->n + kBN - 1) / kBN);   // a ragged last tile reads zero rows of w (TMA OOB fill)
   const int n_items = p.pairs_m * p.tiles_n;
+  p.n_whole = n_items;
+  p.n_halved = 0;
   const size_t smem = sizeof(GemmSmem<kBN, k2Sm>) + 1024;
   auto kern = a->dtype == CSA_DTYPE_BF16 ? csa_gemm_kernel<true, kBN, k2Sm> : csa_gemm_kernel<false, kBN, k2Sm>;
   static bool smem_set[64][2];
@@ -444,7 +473,21 @@ static int gemm_launch(const csa_gemm_args_t* a, GemmParams& p, int dev, int sms
     }
   }
   const int cap = (dev >= 0 && dev < 64) ? max_clusters[dev][ki] : sms / kCl;
-  const int clusters = n_items < cap ? n_items : cap;
+  if constexpr (k2Sm && kBN == 256) {
+    // tail halving: a last wave that fills at most half of the clusters is dealt as twice as many half-width items
+    static const bool halve = []() {
+      const char* e = getenv("CSA_GEMM_TAIL_HALVING");
+      return !(e && atoi(e) == 0);
+    }();
+    const int rem = n_items % cap;
+    if (halve && n_items > cap && rem > 0 && 2 * rem <= cap) {
+      if ((rc = gemm_encode(&p.tm_w_half, a->dtype, a->w, a->n, a->k, a->ldw, kBN / 4))) return rc;
+      p.n_whole = n_items - rem;
+      p.n_halved = rem;
+    }
+  }
+  const int n_work = p.n_whole + 2 * p.n_halved;
+  const int clusters = n_work < cap ? n_work : cap;
   cfg.gridDim = dim3(static_cast<unsigned>(clusters * kCl), 1, 1);
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t ce = cudaLaunchKernelEx(&cfg, kern, p);
