@@ -908,8 +908,8 @@ N1_F16_MS = _n1_f16_ms()
 
 def load_comparator():
     """Best library kernel on the identical compact problem (tools/bench_torch_sdpa.py run on this pool's B200,
-    committed as profiles/r02_sdpa.json): step-equivalent attention time and TFLOP/s, next to ours from the same run."""
-    path = os.path.join(ROOT, "profiles", "r02_sdpa.json")
+    committed as profiles/r03_sdpa.json): step-equivalent attention time and TFLOP/s, next to ours from the same run."""
+    path = os.path.join(ROOT, "profiles", "r03_sdpa.json")
     try:
         with open(path) as f:
             d = json.load(f)
@@ -919,7 +919,7 @@ def load_comparator():
             ms, k = min(cands)
             best[lname] = {"kernel": k, "ms": ms, "tflops": layer["compact"][k]["tflops"],
                            "csa_ms": layer["csa"]["ms"], "csa_tflops": layer["csa"]["tflops"]}
-        return {"source": "profiles/r02_sdpa.json (tools/bench_torch_sdpa.py, same B200 pool, compact per-frame "
+        return {"source": "profiles/r03_sdpa.json (tools/bench_torch_sdpa.py, same B200 pool, compact per-frame "
                           "problem, keys pre-gathered outside the timed region)",
                 "per_layer": best, "step_equivalent": d.get("step_equivalent"),
                 "reference_dense_masked_call": {k: v for k, v in d["layers"]["64x64"]["dense"].items()}}
