@@ -276,6 +276,12 @@ class SpatialAttnProcessor2_0(torch.nn.Module):
         if st is not None:
             st[1].clear()
 
+    def invalidate_native_plan(self) -> None:
+        """Drop the cached stacked weight ``[w_q; w_k; w_v]``.  Needed only after an edit the cache key cannot see: an
+        in-place update THROUGH ``.data`` (``weight.data.copy_(...)``, a manual LoRA merge) changes neither the
+        storage pointer nor the version counter of the parameter."""
+        self.__dict__.pop("_nplan", None)
+
     def _native_plan(self, attn, x):
         """``(key, w_q, w_kv, w_out, b_out, w_qkv)`` when the attn module is the plain SDXL attn1 shape — bias-free Linear
         q/k/v, ``[Linear, Dropout]`` output with the dropout inactive, weights of x's dtype on x's device — else
